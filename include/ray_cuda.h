@@ -1,0 +1,164 @@
+/* ray_cuda.h -- C-ABI of libray_cuda.so: the sm_100a driver layer under Ray::Cuda::Renderer.
+ *
+ * This is the boundary SURVEY.md section 8(b) specifies: `extern "C"`, opaque context, plain pointers and sizes,
+ * caller-owned host memory, int return codes (0 = ok; rc_last_error() explains a failure), no C++ types and no
+ * exceptions across the boundary, one context per device, not thread-safe.  The only intended caller is the C++
+ * Cuda::Renderer (ray_b200/csrc/host, or the binding shown in INTEGRATION.md for the reference tree); tests drive it
+ * through ctypes.
+ *
+ * What each entry point replaces in the reference (file:line relative to the reference tree):
+ *   rc_create/rc_destroy      backend construction in Ray::CreateRenderer (Ray.cpp:53-133; a failing rc_create is
+ *                             what makes Cuda::Renderer's ctor throw so the factory falls through)
+ *   rc_resize / rc_clear      Cpu::Renderer::Resize / Clear (internal/RendererCPU.h:266-301)
+ *   rc_upload_tables          the `rand_seq = __pmj02_samples` argument (internal/RendererCPU.h:445) and
+ *                             filter_table_ (internal/RendererCPU.h:1234-1258)
+ *   rc_upload_scene           construction of scene_data_t from Cpu::Scene's arrays (internal/RendererCPU.h:390-413)
+ *   rc_render                 the body of Cpu::Renderer<P>::RenderScene (internal/RendererCPU.h:374-659):
+ *                             GeneratePrimaryRays, TraceRays, ShadePrimary, TraceShadowRays, the bounce loop with
+ *                             SortRays/TraceRays/ShadeSecondary/TraceShadowRays, accumulate + tonemap + variance
+ *   rc_readback               get_pixels_ref / get_raw_pixels_ref / get_aux_pixels_ref (RendererCPU.h:255-265)
+ *   rc_get_stats              RendererBase::GetStats (RendererBase.h:230-245)
+ *   rc_stage_*                the SIMDPolicy stage functions (internal/RendererCPU.h:39-189) on caller-provided AoS
+ *                             buffers in the reference's own ray_data_t / hit_data_t / shadow_ray_t layouts --
+ *                             test/debug entry points used for per-stage parity against Ref::*
+ */
+#ifndef RAY_CUDA_H
+#define RAY_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rc_ctx rc_ctx;
+
+/* One scene array: pointer to the first element, element count (capacity of the SparseStorage), element size. */
+typedef struct rc_array {
+    const void *ptr;
+    uint32_t count;
+    uint32_t stride;
+} rc_array;
+
+/* View of a finalized wide-BVH Cpu::Scene (reference internal/SceneCPU.h:50-98).  Layouts are the reference's
+ * (internal/Core.h); strides are checked against them. */
+typedef struct rc_scene_view {
+    rc_array wnodes;         /* wbvh_node_t          224 B */
+    rc_array mtris;          /* mtri_accel_t         384 B */
+    rc_array tri_indices;    /* uint32_t               4 B */
+    rc_array tri_materials;  /* tri_mat_data_t         4 B */
+    rc_array materials;      /* material_t            76 B */
+    rc_array mesh_instances; /* mesh_instance_t      144 B */
+    rc_array vertices;       /* vertex_t              44 B */
+    rc_array vtx_indices;    /* uint32_t               4 B */
+    rc_array lights;         /* light_t               64 B */
+    rc_array li_indices;     /* uint32_t               4 B */
+    rc_array light_cwnodes;  /* light_cwbvh_node_t   208 B */
+    uint32_t tlas_root;      /* 0xffffffff = empty scene */
+    uint32_t visible_lights_count, blocker_lights_count;
+    /* environment_t subset (Core.h:393-410) */
+    float env_col[3];
+    uint32_t env_map;        /* must be 0xffffffff: env maps are out of scope */
+    float back_col[3];
+    uint32_t back_map;       /* must be 0xffffffff */
+    uint32_t env_light_index;
+    float sky_map_spread_angle; /* must be 0 */
+    /* Cpu::Scene::GetBounds (ray-sort grid) */
+    float bounds_min[3], bounds_max[3];
+} rc_scene_view;
+
+/* camera_t (reference Types.h:102-115) + pass_settings_t (Types.h:92-100), flattened to 32-bit fields. */
+typedef struct rc_camera {
+    uint32_t type;   /* eCamType: only Persp (0) is supported */
+    uint32_t filter; /* ePixelFilter */
+    uint32_t view_transform; /* eViewTransform: only Standard (0) */
+    float fov, exposure, gamma, sensor_height;
+    float focus_distance, focal_length, fstop, lens_rotation, lens_ratio;
+    int32_t lens_blades;
+    float clip_start, clip_end;
+    float origin[3], fwd[3], side[3], up[3], shift[2];
+    uint32_t max_diff_depth, max_spec_depth, max_refr_depth, max_transp_depth, max_total_depth;
+    uint32_t min_total_depth, min_transp_depth;
+    float clamp_direct, clamp_indirect;
+    int32_t min_samples;
+    float variance_threshold;
+    float regularize_alpha;
+} rc_camera;
+
+typedef struct rc_rect {
+    int32_t x, y, w, h;
+} rc_rect;
+
+enum { RC_RENDER_ASYNC = 1 /* do not synchronise before returning; call rc_sync */,
+       RC_RENDER_NO_SORT = 2 /* skip the results-neutral inter-bounce ray sort */ };
+
+typedef struct rc_pass_desc {
+    rc_camera cam;
+    rc_rect rect;
+    int32_t iteration; /* value of RegionContext::iteration AFTER the increment RenderScene does (>= 1) */
+    uint32_t flags;
+} rc_pass_desc;
+
+enum { RC_BUF_FINAL = 0, RC_BUF_RAW = 1, RC_BUF_BASE_COLOR = 2, RC_BUF_DEPTH_NORMALS = 3, RC_BUF_FULL = 4,
+       RC_BUF_HALF = 5, RC_BUF_TEMP = 6 };
+
+/* Ray bookkeeping of the last rc_render calls since rc_reset_stats: what Mrays/s is computed from. */
+typedef struct rc_counters {
+    uint64_t primary_rays;
+    uint64_t secondary_rays; /* sum over bounces of the rays handed to the closest-hit trace */
+    uint64_t shadow_rays;
+    uint64_t nodes_visited;  /* BVH8 inner nodes box-tested (closest + shadow) */
+    uint64_t leaves_tested;  /* 8-triangle blocks tested */
+    uint64_t samples;        /* rc_render calls */
+} rc_counters;
+
+int rc_device_count(void);
+int rc_create(int device, rc_ctx **out_ctx);
+void rc_destroy(rc_ctx *ctx);
+const char *rc_last_error(const rc_ctx *ctx);
+const char *rc_device_name(const rc_ctx *ctx);
+
+int rc_resize(rc_ctx *ctx, int w, int h);
+int rc_clear(rc_ctx *ctx, const float rgba[4]);
+
+/* pmj: dims*samples*2 uint32 (dims must be 32, samples 4096).  filter_table may be NULL (Box filter). */
+int rc_upload_tables(rc_ctx *ctx, const uint32_t *pmj, int dims, int samples, const float *filter_table,
+                     int filter_table_size);
+int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *scene);
+
+int rc_render(rc_ctx *ctx, const rc_pass_desc *pass);
+int rc_sync(rc_ctx *ctx);
+/* dst: rect.w*rect.h RGBA float pixels written with the given pitch (in pixels). */
+int rc_readback(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch);
+int rc_readback_required_samples(rc_ctx *ctx, uint16_t *dst);
+
+int rc_enable_stats(rc_ctx *ctx, int enable);
+int rc_get_stats(rc_ctx *ctx, uint64_t us[11]); /* order of RendererBase::stats_t */
+int rc_get_counters(rc_ctx *ctx, rc_counters *out);
+int rc_reset_stats(rc_ctx *ctx);
+/* device-side time (ms, CUDA events on the context stream) of each kernel family accumulated since rc_reset_stats:
+ * [0] raygen [1] trace_closest [2] shade [3] trace_shadow [4] sort [5] resolve */
+int rc_get_kernel_ms(rc_ctx *ctx, double ms[6], uint64_t launches[6]);
+
+/* ---- stage entry points (host AoS buffers in the reference's layouts; see header comment) ---- */
+/* rays_out: ray_data_t[rect.w*rect.h] (72 B), hits_out: hit_data_t[...] (20 B); *count_out = rays generated. */
+int rc_stage_generate_primary_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays_out, void *hits_out,
+                                   int *count_out);
+/* rays: in/out (transparency updates c/depth), hits: in/out.  trace_lights != 0 adds IntersectAreaLights. */
+int rc_stage_trace_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays, void *hits, int count, int trace_lights);
+/* primary != 0: ShadePrimary (stores colour, updates AOVs) else ShadeSecondary (adds).  bounce selects the clamp as
+ * RenderScene does.  Outputs are unordered (append order is not the reference's); compare by pixel key `xy`. */
+int rc_stage_shade(rc_ctx *ctx, const rc_pass_desc *pass, int primary, int bounce, const void *rays, const void *hits,
+                   int count, void *secondary_out, int *secondary_count, void *shadow_out, int *shadow_count);
+/* adds the shadow rays' contribution into the TEMP buffer (read it back with rc_readback(RC_BUF_TEMP)) */
+int rc_stage_trace_shadow_rays(rc_ctx *ctx, const rc_pass_desc *pass, const void *shadow_rays, int count,
+                               float clamp_val);
+/* results-neutral: reorders rays in place by the reference's ray hash; returns the hash of each output ray */
+int rc_stage_sort_rays(rc_ctx *ctx, void *rays, int count, uint32_t *hashes_out);
+/* overwrite a rect of the TEMP buffer (stage tests) */
+int rc_debug_fill_temp(rc_ctx *ctx, const float rgba[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAY_CUDA_H */

@@ -1,0 +1,1112 @@
+// ray_cuda.cu -- implementation of the C-ABI in include/ray_cuda.h (libray_cuda.so).
+//
+// Owns the device context: scene arrays, PMJ/filter tables, frame buffers, ray/hit/shadow streams, counters, and the
+// per-sample kernel sequence that stands in for Cpu::Renderer<P>::RenderScene (reference internal/RendererCPU.h:374-659).
+// There is no CPU fallback anywhere in this file: every entry point either runs the sm_100a kernels or fails.
+#include "../../include/ray_cuda.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "rt_kernels.cuh"
+#include "rt_sort.cuh"
+
+using namespace rt;
+
+namespace {
+
+enum { EV_START = 0, EV_RAYGEN, EV_PTRACE, EV_PSHADE, EV_PSHADOW, EV_BOUNCE0 };
+constexpr int kEventsPerBounce = 4; // sort, trace, shade, shadow
+constexpr int kMaxEvents = EV_BOUNCE0 + kEventsPerBounce * kMaxBounces + 2;
+enum { KF_RAYGEN = 0, KF_TRACE, KF_SHADE, KF_SHADOW, KF_SORT, KF_RESOLVE, KF_COUNT };
+
+struct DevArray {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    uint32_t count = 0;
+};
+
+} // namespace
+
+struct rc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string last_error;
+    std::string device_name;
+    int num_sms = 0;
+
+    int w = 0, h = 0;
+    FrameBufs fb{};
+    RayBuf rays[2]{};
+    HitBuf hits{};
+    ShadowBuf shadow{};
+    SortBufs sort{};
+    size_t ray_capacity = 0;
+
+    uint32_t *d_counters = nullptr;
+    unsigned long long *d_totals = nullptr;
+    uint32_t *d_pmj = nullptr;
+    float *d_filter_table = nullptr;
+    bool have_tables = false;
+
+    DevArray wnodes, mtris, tri_indices, tri_materials, materials, mesh_instances, vertices, vtx_indices, lights,
+        light_cwnodes;
+    bool have_scene = false;
+    rc_scene_view scene_info{};
+    uint32_t li_count = 0;
+
+    bool stats_enabled = true;
+    std::vector<cudaEvent_t> events;
+    struct PendingSample {
+        int max_bounces;
+    };
+    bool sample_pending = false;
+    int pending_bounces = 0;
+    uint64_t stats_us[11] = {};
+    double kernel_ms[KF_COUNT] = {};
+    uint64_t kernel_launches[KF_COUNT] = {};
+};
+
+namespace {
+
+int fail(rc_ctx *ctx, const char *fmt, ...) {
+    char buf[1024];
+    va_list vl;
+    va_start(vl, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, vl);
+    va_end(vl);
+    if (ctx) {
+        ctx->last_error = buf;
+    }
+    return 1;
+}
+
+#define CU_CHECK(ctx, call)                                                                                            \
+    do {                                                                                                               \
+        const cudaError_t _e = (call);                                                                                 \
+        if (_e != cudaSuccess) {                                                                                       \
+            return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);              \
+        }                                                                                                              \
+    } while (0)
+
+template <typename T> int dev_alloc(rc_ctx *ctx, T **p, size_t count) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (count == 0) {
+        return 0;
+    }
+    CU_CHECK(ctx, cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T)));
+    return 0;
+}
+
+int upload_array(rc_ctx *ctx, DevArray &dst, const rc_array &src, uint32_t expected_stride, const char *name) {
+    if (src.count != 0 && src.stride != expected_stride) {
+        return fail(ctx, "rc_upload_scene: %s stride %u != %u", name, src.stride, expected_stride);
+    }
+    if (dst.ptr) {
+        cudaFree(dst.ptr);
+        dst = DevArray{};
+    }
+    dst.count = src.count;
+    dst.bytes = size_t(src.count) * expected_stride;
+    if (dst.bytes == 0) {
+        // keep a valid non-null pointer so kernels can form (never dereferenced) addresses
+        CU_CHECK(ctx, cudaMalloc(&dst.ptr, 256));
+        CU_CHECK(ctx, cudaMemsetAsync(dst.ptr, 0, 256, ctx->stream));
+        return 0;
+    }
+    if (!src.ptr) {
+        return fail(ctx, "rc_upload_scene: %s has count %u but a null pointer", name, src.count);
+    }
+    CU_CHECK(ctx, cudaMalloc(&dst.ptr, dst.bytes));
+    CU_CHECK(ctx, cudaMemcpyAsync(dst.ptr, src.ptr, dst.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int alloc_ray_buf(rc_ctx *ctx, RayBuf &b, size_t n) {
+    if (dev_alloc(ctx, &b.o_cw, n) || dev_alloc(ctx, &b.d_cs, n) || dev_alloc(ctx, &b.c_pdf, n) ||
+        dev_alloc(ctx, &b.ior, n) || dev_alloc(ctx, &b.xy_depth, n)) {
+        return 1;
+    }
+    return 0;
+}
+
+void free_ray_buf(RayBuf &b) {
+    cudaFree(b.o_cw);
+    cudaFree(b.d_cs);
+    cudaFree(b.c_pdf);
+    cudaFree(b.ior);
+    cudaFree(b.xy_depth);
+    b = RayBuf{};
+}
+
+// murmur3 finaliser on the host (reference CoreRef.h:133-141) for rand_seed = hash((iteration - 1) / 4096)
+uint32_t host_hash(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+
+int host_popcount(unsigned x) {
+    int c = 0;
+    for (; x != 0; x &= x - 1) {
+        c++;
+    }
+    return c;
+}
+
+int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
+    if (!ctx->have_scene) {
+        return fail(ctx, "no scene uploaded");
+    }
+    if (!ctx->have_tables) {
+        return fail(ctx, "no sampler table uploaded (rc_upload_tables)");
+    }
+    if (ctx->w == 0 || ctx->h == 0) {
+        return fail(ctx, "frame buffer has zero size (rc_resize)");
+    }
+    const rc_camera &c = pass->cam;
+    if (c.type != 0) {
+        return fail(ctx, "camera type %u is not supported by the CUDA backend (only Persp)", c.type);
+    }
+    if (c.view_transform != 0) {
+        return fail(ctx, "view transform %u is not supported by the CUDA backend (only Standard)", c.view_transform);
+    }
+    if (c.filter != 0 && !ctx->d_filter_table) {
+        return fail(ctx, "pixel filter %u needs a filter table (rc_upload_tables)", c.filter);
+    }
+    if (c.max_total_depth + 1 >= uint32_t(kMaxBounces)) {
+        return fail(ctx, "max_total_depth %u exceeds the backend limit %d", c.max_total_depth, kMaxBounces - 2);
+    }
+    const rc_rect &r = pass->rect;
+    if (r.x < 0 || r.y < 0 || r.w <= 0 || r.h <= 0 || r.x + r.w > ctx->w || r.y + r.h > ctx->h) {
+        return fail(ctx, "rect (%d,%d,%d,%d) is outside the %dx%d frame", r.x, r.y, r.w, r.h, ctx->w, ctx->h);
+    }
+    if (pass->iteration < 1) {
+        return fail(ctx, "iteration must be >= 1");
+    }
+
+    memset(&p, 0, sizeof(p));
+    p.sc.geo.nodes = static_cast<const WNode *>(ctx->wnodes.ptr);
+    p.sc.geo.mtris = static_cast<const MTri *>(ctx->mtris.ptr);
+    p.sc.geo.tri_indices = static_cast<const uint32_t *>(ctx->tri_indices.ptr);
+    p.sc.geo.tri_materials = static_cast<const TriMat *>(ctx->tri_materials.ptr);
+    p.sc.geo.instances = static_cast<const MeshInstance *>(ctx->mesh_instances.ptr);
+    p.sc.geo.tlas_root = ctx->scene_info.tlas_root;
+    p.sc.surf.vertices = static_cast<const Vertex *>(ctx->vertices.ptr);
+    p.sc.surf.vtx_indices = static_cast<const uint32_t *>(ctx->vtx_indices.ptr);
+    p.sc.surf.materials = static_cast<const Material *>(ctx->materials.ptr);
+    p.sc.lights.lights = static_cast<const Light *>(ctx->lights.ptr);
+    p.sc.lights.nodes = static_cast<const LightCWNode *>(ctx->light_cwnodes.ptr);
+    p.sc.lights.nodes_count = ctx->light_cwnodes.count;
+    p.sc.lights.visible_lights_count = ctx->scene_info.visible_lights_count;
+    p.sc.lights.blocker_lights_count = ctx->scene_info.blocker_lights_count;
+    p.sc.lights.env_light_index = ctx->scene_info.env_light_index;
+    for (int i = 0; i < 3; ++i) {
+        p.sc.lights.env_col[i] = ctx->scene_info.env_col[i];
+        p.sc.lights.back_col[i] = ctx->scene_info.back_col[i];
+    }
+    p.sc.rand_seq = ctx->d_pmj;
+    p.sc.li_count = ctx->li_count;
+
+    p.ps.max_diff_depth = int(c.max_diff_depth);
+    p.ps.max_spec_depth = int(c.max_spec_depth);
+    p.ps.max_refr_depth = int(c.max_refr_depth);
+    p.ps.max_transp_depth = int(c.max_transp_depth);
+    p.ps.max_total_depth = int(c.max_total_depth);
+    p.ps.min_total_depth = int(c.min_total_depth);
+    p.ps.min_transp_depth = int(c.min_transp_depth);
+    p.ps.clamp_direct = c.clamp_direct;
+    p.ps.clamp_indirect = c.clamp_indirect;
+    p.ps.regularize_alpha = c.regularize_alpha;
+
+    // camera-derived constants, computed with the host libm exactly like GeneratePrimaryRays (CoreRef.cpp:1434-1442)
+    const float PI = 3.141592653589793238463f;
+    p.cam.origin = v3{c.origin[0], c.origin[1], c.origin[2]};
+    p.cam.fwd = v3{c.fwd[0], c.fwd[1], c.fwd[2]};
+    p.cam.side = v3{c.side[0], c.side[1], c.side[2]};
+    p.cam.up = v3{c.up[0], c.up[1], c.up[2]};
+    p.cam.shift_x = c.shift[0];
+    p.cam.shift_y = c.shift[1];
+    p.cam.focus_distance = c.focus_distance;
+    p.cam.k = float(ctx->w) / float(ctx->h);
+    const float temp = tanf(0.5f * c.fov * PI / 180.0f);
+    p.cam.fov_k = temp * c.focus_distance;
+    p.cam.spread_angle = atanf(2.0f * temp / float(ctx->h));
+    p.cam.fstop = c.fstop;
+    p.cam.focal_length = c.focal_length;
+    p.cam.sensor_height = c.sensor_height;
+    p.cam.lens_rotation = c.lens_rotation;
+    p.cam.lens_ratio = c.lens_ratio;
+    p.cam.lens_blades = c.lens_blades;
+    p.cam.clip_start = c.clip_start;
+    p.cam.clip_end = c.clip_end;
+    p.cam.filter = int(c.filter);
+
+    p.fb = ctx->fb;
+    p.filter_table = ctx->d_filter_table;
+    p.counters = ctx->d_counters;
+    p.totals = ctx->d_totals;
+    p.rect_x = r.x;
+    p.rect_y = r.y;
+    p.rect_w = r.w;
+    p.rect_h = r.h;
+    p.iteration = pass->iteration;
+    p.rand_seed = host_hash(uint32_t((pass->iteration - 1) / kRandSamples));
+    return 0;
+}
+
+float clamp_limit(float v) { return (v != 0.0f) ? 3.0f * v : 3.402823466e+38F; }
+
+int persistent_grid(const rc_ctx *ctx, int blocks_per_sm) { return ctx->num_sms * blocks_per_sm; }
+
+void record(rc_ctx *ctx, int ev) {
+    if (ctx->stats_enabled) {
+        cudaEventRecord(ctx->events[ev], ctx->stream);
+    }
+}
+
+// fold the event timings of the last enqueued sample into stats_t / per-kernel totals
+int harvest_stats(rc_ctx *ctx) {
+    if (!ctx->sample_pending || !ctx->stats_enabled) {
+        ctx->sample_pending = false;
+        return 0;
+    }
+    ctx->sample_pending = false;
+    auto ms = [&](int a, int b) {
+        float v = 0.0f;
+        cudaEventElapsedTime(&v, ctx->events[a], ctx->events[b]);
+        return double(v);
+    };
+    const double raygen = ms(EV_START, EV_RAYGEN), ptrace = ms(EV_RAYGEN, EV_PTRACE), pshade = ms(EV_PTRACE, EV_PSHADE),
+                 pshadow = ms(EV_PSHADE, EV_PSHADOW);
+    double ssort = 0, strace = 0, sshade = 0, sshadow = 0;
+    int prev = EV_PSHADOW;
+    for (int b = 0; b < ctx->pending_bounces; ++b) {
+        const int e = EV_BOUNCE0 + b * kEventsPerBounce;
+        ssort += ms(prev, e + 0);
+        strace += ms(e + 0, e + 1);
+        sshade += ms(e + 1, e + 2);
+        sshadow += ms(e + 2, e + 3);
+        prev = e + 3;
+    }
+    const int e_end = EV_BOUNCE0 + kEventsPerBounce * kMaxBounces;
+    const double resolve = ms(prev, e_end);
+    ctx->stats_us[0] += uint64_t(raygen * 1000.0);
+    ctx->stats_us[1] += uint64_t(ptrace * 1000.0);
+    ctx->stats_us[2] += uint64_t(pshade * 1000.0);
+    ctx->stats_us[3] += uint64_t(pshadow * 1000.0);
+    ctx->stats_us[4] += uint64_t(ssort * 1000.0);
+    ctx->stats_us[5] += uint64_t(strace * 1000.0);
+    ctx->stats_us[6] += uint64_t(sshade * 1000.0);
+    ctx->stats_us[7] += uint64_t(sshadow * 1000.0);
+    ctx->kernel_ms[KF_RAYGEN] += raygen;
+    ctx->kernel_ms[KF_TRACE] += ptrace + strace;
+    ctx->kernel_ms[KF_SHADE] += pshade + sshade;
+    ctx->kernel_ms[KF_SHADOW] += pshadow + sshadow;
+    ctx->kernel_ms[KF_SORT] += ssort;
+    ctx->kernel_ms[KF_RESOLVE] += resolve;
+    return 0;
+}
+
+// Enqueue the kernels of one sample.
+int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
+    cudaStream_t s = ctx->stream;
+    const int max_bounces = p.ps.max_total_depth;
+    const bool do_sort = (pass->flags & RC_RENDER_NO_SORT) == 0;
+
+    if (ctx->sample_pending) {
+        // event slots are reused per sample: collect the previous sample's timings first
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        harvest_stats(ctx);
+    }
+
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), s));
+    record(ctx, EV_START);
+
+    const int n_pix_tiles = ((p.rect_w + 7) / 8) * ((p.rect_h + 3) / 4);
+    const int raygen_blocks = (n_pix_tiles * 32 + 255) / 256;
+    k_raygen<<<raygen_blocks, 256, 0, s>>>(p, ctx->rays[0], ctx->hits);
+    ctx->kernel_launches[KF_RAYGEN]++;
+    record(ctx, EV_RAYGEN);
+
+    const int trace_grid = persistent_grid(ctx, 8);
+    const int shade_grid = persistent_grid(ctx, 4);
+    const bool have_geo = ctx->scene_info.tlas_root != 0xffffffffu;
+
+    if (have_geo) {
+        k_trace_closest<false, false><<<trace_grid, 128, 0, s>>>(p, ctx->rays[0], ctx->hits, 0);
+        ctx->kernel_launches[KF_TRACE]++;
+    }
+    record(ctx, EV_PTRACE);
+
+    const float mix_factor = 1.0f / float(p.iteration);
+    {
+        const float lim = clamp_limit(p.ps.clamp_direct);
+        k_shade<true><<<shade_grid, 128, 0, s>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
+                                                  mix_factor);
+        ctx->kernel_launches[KF_SHADE]++;
+    }
+    record(ctx, EV_PSHADE);
+
+    if (have_geo) {
+        k_trace_shadow<<<trace_grid, 128, 0, s>>>(p, ctx->shadow, 0, clamp_limit(p.ps.clamp_direct));
+        ctx->kernel_launches[KF_SHADOW]++;
+    }
+    record(ctx, EV_PSHADOW);
+
+    int cur = 1; // list index holding the rays of the current bounce
+    for (int bounce = 1; bounce <= max_bounces; ++bounce) {
+        const int e = EV_BOUNCE0 + (bounce - 1) * kEventsPerBounce;
+        if (do_sort) {
+            sort_rays(ctx->sort, p, ctx->rays[cur], ctx->rays[cur ^ 1], bounce, ctx->num_sms, s);
+            cur ^= 1; // the reordered list now lives in the other buffer; the old one is free for this bounce's output
+            ctx->kernel_launches[KF_SORT] += 3;
+        }
+        record(ctx, e + 0);
+        if (have_geo) {
+            if (ctx->scene_info.visible_lights_count != 0) {
+                k_trace_closest<true, true><<<trace_grid, 128, 0, s>>>(p, ctx->rays[cur], ctx->hits, bounce);
+            } else {
+                k_trace_closest<false, true><<<trace_grid, 128, 0, s>>>(p, ctx->rays[cur], ctx->hits, bounce);
+            }
+        } else {
+            k_init_hits<<<shade_grid, 128, 0, s>>>(p, ctx->hits, bounce);
+        }
+        ctx->kernel_launches[KF_TRACE]++;
+        record(ctx, e + 1);
+        {
+            const float cd = (bounce == 1) ? p.ps.clamp_direct : p.ps.clamp_indirect;
+            k_shade<false><<<shade_grid, 128, 0, s>>>(p, ctx->rays[cur], ctx->hits, ctx->rays[cur ^ 1], ctx->shadow,
+                                                       bounce, clamp_limit(cd), clamp_limit(p.ps.clamp_indirect),
+                                                       mix_factor);
+            ctx->kernel_launches[KF_SHADE]++;
+        }
+        record(ctx, e + 2);
+        if (have_geo) {
+            k_trace_shadow<<<trace_grid, 128, 0, s>>>(p, ctx->shadow, bounce, clamp_limit(p.ps.clamp_indirect));
+            ctx->kernel_launches[KF_SHADOW]++;
+        }
+        record(ctx, e + 3);
+        cur ^= 1;
+    }
+
+    {
+        const float exposure_mul = powf(2.0f, pass->cam.exposure);
+        const int is_class_a = host_popcount(uint32_t(p.iteration - 1) & 0xaaaaaaaau) & 1;
+        const float half_mix_factor = 1.0f / float((p.iteration + 1) / 2);
+        const float inv_gamma = 1.0f / pass->cam.gamma;
+        const float vt = p.iteration > pass->cam.min_samples
+                             ? 0.5f * pass->cam.variance_threshold * pass->cam.variance_threshold
+                             : 0.0f;
+        const int n = p.rect_w * p.rect_h;
+        k_resolve<<<(n + 255) / 256, 256, 0, s>>>(p, exposure_mul, mix_factor, half_mix_factor, is_class_a, inv_gamma, vt);
+        ctx->kernel_launches[KF_RESOLVE]++;
+        k_accumulate_totals<<<1, 32, 0, s>>>(p, max_bounces);
+    }
+    record(ctx, EV_BOUNCE0 + kEventsPerBounce * kMaxBounces);
+    ctx->sample_pending = true;
+    ctx->pending_bounces = max_bounces;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// ---- AoS <-> SoA staging for the stage entry points ----------------------------------------------------------------
+int upload_rays_aos(rc_ctx *ctx, const RayBuf &b, const RayAoS *src, int n) {
+    std::vector<float4> p0(n), p1(n), p2(n), p3(n);
+    std::vector<uint2> p4(n);
+    for (int i = 0; i < n; ++i) {
+        const RayAoS &r = src[i];
+        p0[i] = make_float4(r.o[0], r.o[1], r.o[2], r.cone_width);
+        p1[i] = make_float4(r.d[0], r.d[1], r.d[2], r.cone_spread);
+        p2[i] = make_float4(r.c[0], r.c[1], r.c[2], r.pdf);
+        p3[i] = make_float4(r.ior[0], r.ior[1], r.ior[2], r.ior[3]);
+        p4[i] = make_uint2(r.xy, r.depth);
+    }
+    CU_CHECK(ctx, cudaMemcpy(b.o_cw, p0.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.d_cs, p1.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.c_pdf, p2.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.ior, p3.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.xy_depth, p4.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int download_rays_aos(rc_ctx *ctx, const RayBuf &b, RayAoS *dst, int n) {
+    std::vector<float4> p0(n), p1(n), p2(n), p3(n);
+    std::vector<uint2> p4(n);
+    CU_CHECK(ctx, cudaMemcpy(p0.data(), b.o_cw, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p1.data(), b.d_cs, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p2.data(), b.c_pdf, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p3.data(), b.ior, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p4.data(), b.xy_depth, n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        RayAoS &r = dst[i];
+        r.o[0] = p0[i].x, r.o[1] = p0[i].y, r.o[2] = p0[i].z, r.cone_width = p0[i].w;
+        r.d[0] = p1[i].x, r.d[1] = p1[i].y, r.d[2] = p1[i].z, r.cone_spread = p1[i].w;
+        r.c[0] = p2[i].x, r.c[1] = p2[i].y, r.c[2] = p2[i].z, r.pdf = p2[i].w;
+        r.ior[0] = p3[i].x, r.ior[1] = p3[i].y, r.ior[2] = p3[i].z, r.ior[3] = p3[i].w;
+        r.xy = p4[i].x, r.depth = p4[i].y;
+    }
+    return 0;
+}
+
+int upload_hits_aos(rc_ctx *ctx, const HitBuf &b, const HitAoS *src, int n) {
+    std::vector<float4> p0(n);
+    std::vector<int> p1(n);
+    for (int i = 0; i < n; ++i) {
+        float pf;
+        memcpy(&pf, &src[i].prim_index, 4);
+        p0[i] = make_float4(src[i].t, src[i].u, src[i].v, pf);
+        p1[i] = src[i].obj_index;
+    }
+    CU_CHECK(ctx, cudaMemcpy(b.tuvp, p0.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.obj, p1.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int download_hits_aos(rc_ctx *ctx, const HitBuf &b, HitAoS *dst, int n) {
+    std::vector<float4> p0(n);
+    std::vector<int> p1(n);
+    CU_CHECK(ctx, cudaMemcpy(p0.data(), b.tuvp, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p1.data(), b.obj, n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        dst[i].t = p0[i].x, dst[i].u = p0[i].y, dst[i].v = p0[i].z;
+        memcpy(&dst[i].prim_index, &p0[i].w, 4);
+        dst[i].obj_index = p1[i];
+    }
+    return 0;
+}
+
+int upload_shadow_aos(rc_ctx *ctx, const ShadowBuf &b, const ShadowRayAoS *src, int n) {
+    std::vector<float4> p0(n), p1(n), p2(n);
+    for (int i = 0; i < n; ++i) {
+        float df, xf;
+        memcpy(&df, &src[i].depth, 4);
+        memcpy(&xf, &src[i].xy, 4);
+        p0[i] = make_float4(src[i].o[0], src[i].o[1], src[i].o[2], df);
+        p1[i] = make_float4(src[i].d[0], src[i].d[1], src[i].d[2], src[i].dist);
+        p2[i] = make_float4(src[i].c[0], src[i].c[1], src[i].c[2], xf);
+    }
+    CU_CHECK(ctx, cudaMemcpy(b.o_depth, p0.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.d_dist, p1.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU_CHECK(ctx, cudaMemcpy(b.c_xy, p2.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int download_shadow_aos(rc_ctx *ctx, const ShadowBuf &b, ShadowRayAoS *dst, int n) {
+    std::vector<float4> p0(n), p1(n), p2(n);
+    CU_CHECK(ctx, cudaMemcpy(p0.data(), b.o_depth, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p1.data(), b.d_dist, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU_CHECK(ctx, cudaMemcpy(p2.data(), b.c_xy, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        dst[i].o[0] = p0[i].x, dst[i].o[1] = p0[i].y, dst[i].o[2] = p0[i].z;
+        memcpy(&dst[i].depth, &p0[i].w, 4);
+        dst[i].d[0] = p1[i].x, dst[i].d[1] = p1[i].y, dst[i].d[2] = p1[i].z, dst[i].dist = p1[i].w;
+        dst[i].c[0] = p2[i].x, dst[i].c[1] = p2[i].y, dst[i].c[2] = p2[i].z;
+        memcpy(&dst[i].xy, &p2[i].w, 4);
+    }
+    return 0;
+}
+
+int set_counter(rc_ctx *ctx, int slot, uint32_t v) {
+    CU_CHECK(ctx, cudaMemcpy(ctx->d_counters + slot, &v, sizeof(v), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int get_counter(rc_ctx *ctx, int slot, uint32_t *v) {
+    CU_CHECK(ctx, cudaMemcpy(v, ctx->d_counters + slot, sizeof(*v), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int rc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rc_create(int device, rc_ctx **out_ctx) {
+    if (!out_ctx) {
+        return 1;
+    }
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        return 2; // no such device: Cuda::Renderer's ctor turns this into std::runtime_error
+    }
+    rc_ctx *ctx = new rc_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+        delete ctx;
+        return 3;
+    }
+    if (ctx->prop.major < 10) {
+        // the fatbin only holds sm_100a code
+        delete ctx;
+        return 4;
+    }
+    ctx->device_name = ctx->prop.name;
+    ctx->num_sms = ctx->prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return 5;
+    }
+    ctx->events.resize(kMaxEvents);
+    for (auto &e : ctx->events) {
+        cudaEventCreate(&e);
+    }
+    if (dev_alloc(ctx, &ctx->d_counters, CNT_TOTAL) || dev_alloc(ctx, &ctx->d_totals, TOT_COUNT)) {
+        rc_destroy(ctx);
+        return 6;
+    }
+    cudaMemset(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t));
+    cudaMemset(ctx->d_totals, 0, TOT_COUNT * sizeof(unsigned long long));
+    // traversal stacks live in local memory: give L1 the whole carve-out
+    cudaFuncSetAttribute(k_trace_closest<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace_closest<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace_shadow, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    *out_ctx = ctx;
+    return 0;
+}
+
+void rc_destroy(rc_ctx *ctx) {
+    if (!ctx) {
+        return;
+    }
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    for (auto &e : ctx->events) {
+        cudaEventDestroy(e);
+    }
+    cudaFree(ctx->fb.temp);
+    cudaFree(ctx->fb.full);
+    cudaFree(ctx->fb.half);
+    cudaFree(ctx->fb.raw);
+    cudaFree(ctx->fb.final);
+    cudaFree(ctx->fb.base_color);
+    cudaFree(ctx->fb.depth_normals);
+    cudaFree(ctx->fb.required_samples);
+    free_ray_buf(ctx->rays[0]);
+    free_ray_buf(ctx->rays[1]);
+    cudaFree(ctx->hits.tuvp);
+    cudaFree(ctx->hits.obj);
+    cudaFree(ctx->shadow.o_depth);
+    cudaFree(ctx->shadow.d_dist);
+    cudaFree(ctx->shadow.c_xy);
+    free_sort_bufs(ctx->sort);
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_totals);
+    cudaFree(ctx->d_pmj);
+    cudaFree(ctx->d_filter_table);
+    for (DevArray *a : {&ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
+                        &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes}) {
+        cudaFree(a->ptr);
+    }
+    if (ctx->stream) {
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char *rc_last_error(const rc_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char *rc_device_name(const rc_ctx *ctx) { return ctx ? ctx->device_name.c_str() : ""; }
+
+int rc_resize(rc_ctx *ctx, int w, int h) {
+    if (!ctx || w < 0 || h < 0 || w > 65535 || h > 65535) {
+        return fail(ctx, "rc_resize: bad size %dx%d", w, h);
+    }
+    cudaSetDevice(ctx->device);
+    if (w == ctx->w && h == ctx->h) {
+        return 0; // idempotent like Cpu::Renderer::Resize (RendererCPU.h:266-295)
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = size_t(w) * h;
+    if (dev_alloc(ctx, &ctx->fb.temp, n) || dev_alloc(ctx, &ctx->fb.full, n) || dev_alloc(ctx, &ctx->fb.half, n) ||
+        dev_alloc(ctx, &ctx->fb.raw, n) || dev_alloc(ctx, &ctx->fb.final, n) || dev_alloc(ctx, &ctx->fb.base_color, n) ||
+        dev_alloc(ctx, &ctx->fb.depth_normals, n) || dev_alloc(ctx, &ctx->fb.required_samples, n)) {
+        return 1;
+    }
+    if (n) {
+        for (float4 *b : {ctx->fb.temp, ctx->fb.full, ctx->fb.half, ctx->fb.raw, ctx->fb.final, ctx->fb.base_color,
+                          ctx->fb.depth_normals}) {
+            CU_CHECK(ctx, cudaMemsetAsync(b, 0, n * sizeof(float4), ctx->stream));
+        }
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->fb.required_samples, 0xff, n * sizeof(uint16_t), ctx->stream));
+    }
+    if (alloc_ray_buf(ctx, ctx->rays[0], n) || alloc_ray_buf(ctx, ctx->rays[1], n) || dev_alloc(ctx, &ctx->hits.tuvp, n) ||
+        dev_alloc(ctx, &ctx->hits.obj, n) || dev_alloc(ctx, &ctx->shadow.o_depth, n) ||
+        dev_alloc(ctx, &ctx->shadow.d_dist, n) || dev_alloc(ctx, &ctx->shadow.c_xy, n)) {
+        return 1;
+    }
+    if (alloc_sort_bufs(ctx->sort, n) != 0) {
+        return fail(ctx, "rc_resize: sort buffer allocation failed");
+    }
+    ctx->ray_capacity = n;
+    ctx->fb.w = w;
+    ctx->fb.h = h;
+    ctx->w = w;
+    ctx->h = h;
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+__global__ void k_fill4(float4 *dst, float4 v, size_t n) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        dst[i] = v;
+    }
+}
+
+int rc_clear(rc_ctx *ctx, const float rgba[4]) {
+    if (!ctx) {
+        return 1;
+    }
+    cudaSetDevice(ctx->device);
+    const size_t n = size_t(ctx->w) * ctx->h;
+    if (n == 0) {
+        return 0;
+    }
+    const float4 v = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+    k_fill4<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->fb.full, v, n);
+    k_fill4<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->fb.half, v, n);
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->fb.required_samples, 0xff, n * sizeof(uint16_t), ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rc_debug_fill_temp(rc_ctx *ctx, const float rgba[4]) {
+    if (!ctx) {
+        return 1;
+    }
+    cudaSetDevice(ctx->device);
+    const size_t n = size_t(ctx->w) * ctx->h;
+    if (n == 0) {
+        return 0;
+    }
+    k_fill4<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->fb.temp, make_float4(rgba[0], rgba[1], rgba[2], rgba[3]), n);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rc_upload_tables(rc_ctx *ctx, const uint32_t *pmj, int dims, int samples, const float *filter_table,
+                     int filter_table_size) {
+    if (!ctx || !pmj) {
+        return fail(ctx, "rc_upload_tables: null argument");
+    }
+    if (dims != kRandDims || samples != kRandSamples) {
+        return fail(ctx, "rc_upload_tables: table must be %d dims x %d samples", kRandDims, kRandSamples);
+    }
+    cudaSetDevice(ctx->device);
+    const size_t n = size_t(dims) * samples * 2;
+    if (dev_alloc(ctx, &ctx->d_pmj, n)) {
+        return 1;
+    }
+    CU_CHECK(ctx, cudaMemcpy(ctx->d_pmj, pmj, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (filter_table) {
+        if (filter_table_size != kFilterTableSize) {
+            return fail(ctx, "rc_upload_tables: filter table must have %d entries", kFilterTableSize);
+        }
+        if (dev_alloc(ctx, &ctx->d_filter_table, size_t(kFilterTableSize))) {
+            return 1;
+        }
+        CU_CHECK(ctx, cudaMemcpy(ctx->d_filter_table, filter_table, kFilterTableSize * sizeof(float),
+                                 cudaMemcpyHostToDevice));
+    }
+    ctx->have_tables = true;
+    return 0;
+}
+
+int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
+    if (!ctx || !sv) {
+        return fail(ctx, "rc_upload_scene: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    if (sv->env_map != 0xffffffffu || sv->back_map != 0xffffffffu) {
+        return fail(ctx, "rc_upload_scene: environment maps are not supported by the CUDA backend");
+    }
+    if (sv->sky_map_spread_angle != 0.0f) {
+        return fail(ctx, "rc_upload_scene: procedural sky is not supported by the CUDA backend");
+    }
+    // textures are out of scope: reject instead of silently rendering something else
+    if (sv->materials.ptr && sv->materials.stride == sizeof(Material)) {
+        const Material *m = static_cast<const Material *>(sv->materials.ptr);
+        // NOTE: callers pass `count` = number of live, contiguous slots (SparseStorage::size() when nothing was
+        // removed); slots past that are uninitialised in the reference's storage and must not be handed over.
+        for (uint32_t i = 0; i < sv->materials.count; ++i) {
+            if (m[i].type > NODE_PRINCIPLED) {
+                continue;
+            }
+            const bool is_mix = (m[i].type == NODE_MIX);
+            for (int t = 0; t < 5; ++t) {
+                if (is_mix && (t == kMixMat1 || t == kMixMat2)) {
+                    continue;
+                }
+                if (m[i].textures[t] != 0xffffffffu) {
+                    return fail(ctx, "rc_upload_scene: material %u uses texture slot %d; textures are not supported "
+                                     "by the CUDA backend",
+                                i, t);
+                }
+            }
+        }
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (upload_array(ctx, ctx->wnodes, sv->wnodes, sizeof(WNode), "wnodes") ||
+        upload_array(ctx, ctx->mtris, sv->mtris, sizeof(MTri), "mtris") ||
+        upload_array(ctx, ctx->tri_indices, sv->tri_indices, 4, "tri_indices") ||
+        upload_array(ctx, ctx->tri_materials, sv->tri_materials, sizeof(TriMat), "tri_materials") ||
+        upload_array(ctx, ctx->materials, sv->materials, sizeof(Material), "materials") ||
+        upload_array(ctx, ctx->mesh_instances, sv->mesh_instances, sizeof(MeshInstance), "mesh_instances") ||
+        upload_array(ctx, ctx->vertices, sv->vertices, sizeof(Vertex), "vertices") ||
+        upload_array(ctx, ctx->vtx_indices, sv->vtx_indices, 4, "vtx_indices") ||
+        upload_array(ctx, ctx->lights, sv->lights, sizeof(Light), "lights") ||
+        upload_array(ctx, ctx->light_cwnodes, sv->light_cwnodes, sizeof(LightCWNode), "light_cwnodes")) {
+        return 1;
+    }
+    ctx->scene_info = *sv;
+    ctx->li_count = sv->li_indices.count;
+    set_sort_bounds(ctx->sort, sv->bounds_min, sv->bounds_max);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_scene = true;
+    return 0;
+}
+
+int rc_render(rc_ctx *ctx, const rc_pass_desc *pass) {
+    if (!ctx || !pass) {
+        return fail(ctx, "rc_render: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    KParams p;
+    if (fill_params(ctx, pass, p)) {
+        return 1;
+    }
+    if (enqueue_sample(ctx, pass, p)) {
+        return 1;
+    }
+    if ((pass->flags & RC_RENDER_ASYNC) == 0) {
+        return rc_sync(ctx);
+    }
+    return 0;
+}
+
+int rc_sync(rc_ctx *ctx) {
+    if (!ctx) {
+        return 1;
+    }
+    cudaSetDevice(ctx->device);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    harvest_stats(ctx);
+    return 0;
+}
+
+int rc_readback(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch) {
+    if (!ctx || !rect || !dst) {
+        return fail(ctx, "rc_readback: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    const float4 *src = nullptr;
+    switch (which) {
+    case RC_BUF_FINAL: src = ctx->fb.final; break;
+    case RC_BUF_RAW: src = ctx->fb.raw; break;
+    case RC_BUF_BASE_COLOR: src = ctx->fb.base_color; break;
+    case RC_BUF_DEPTH_NORMALS: src = ctx->fb.depth_normals; break;
+    case RC_BUF_FULL: src = ctx->fb.full; break;
+    case RC_BUF_HALF: src = ctx->fb.half; break;
+    case RC_BUF_TEMP: src = ctx->fb.temp; break;
+    default: return fail(ctx, "rc_readback: unknown buffer %d", which);
+    }
+    if (rect->x < 0 || rect->y < 0 || rect->w <= 0 || rect->h <= 0 || rect->x + rect->w > ctx->w ||
+        rect->y + rect->h > ctx->h || pitch < rect->w) {
+        return fail(ctx, "rc_readback: bad rect/pitch");
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaMemcpy2D(dst, size_t(pitch) * sizeof(float4), src + size_t(rect->y) * ctx->w + rect->x,
+                               size_t(ctx->w) * sizeof(float4), size_t(rect->w) * sizeof(float4), rect->h,
+                               cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rc_readback_required_samples(rc_ctx *ctx, uint16_t *dst) {
+    if (!ctx || !dst) {
+        return 1;
+    }
+    cudaSetDevice(ctx->device);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaMemcpy(dst, ctx->fb.required_samples, size_t(ctx->w) * ctx->h * sizeof(uint16_t),
+                             cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rc_enable_stats(rc_ctx *ctx, int enable) {
+    if (!ctx) {
+        return 1;
+    }
+    rc_sync(ctx);
+    ctx->stats_enabled = enable != 0;
+    return 0;
+}
+
+int rc_get_stats(rc_ctx *ctx, uint64_t us[11]) {
+    if (!ctx || !us) {
+        return 1;
+    }
+    rc_sync(ctx);
+    memcpy(us, ctx->stats_us, sizeof(ctx->stats_us));
+    return 0;
+}
+
+int rc_get_counters(rc_ctx *ctx, rc_counters *out) {
+    if (!ctx || !out) {
+        return 1;
+    }
+    cudaSetDevice(ctx->device);
+    rc_sync(ctx);
+    unsigned long long t[TOT_COUNT];
+    CU_CHECK(ctx, cudaMemcpy(t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+    out->primary_rays = t[TOT_PRIMARY];
+    out->secondary_rays = t[TOT_SECONDARY];
+    out->shadow_rays = t[TOT_SHADOW];
+    out->nodes_visited = t[TOT_NODES];
+    out->leaves_tested = t[TOT_LEAVES];
+    out->samples = t[TOT_SAMPLES];
+    return 0;
+}
+
+int rc_reset_stats(rc_ctx *ctx) {
+    if (!ctx) {
+        return 1;
+    }
+    cudaSetDevice(ctx->device);
+    rc_sync(ctx);
+    memset(ctx->stats_us, 0, sizeof(ctx->stats_us));
+    memset(ctx->kernel_ms, 0, sizeof(ctx->kernel_ms));
+    memset(ctx->kernel_launches, 0, sizeof(ctx->kernel_launches));
+    CU_CHECK(ctx, cudaMemset(ctx->d_totals, 0, TOT_COUNT * sizeof(unsigned long long)));
+    return 0;
+}
+
+int rc_get_kernel_ms(rc_ctx *ctx, double ms[6], uint64_t launches[6]) {
+    if (!ctx) {
+        return 1;
+    }
+    rc_sync(ctx);
+    for (int i = 0; i < KF_COUNT; ++i) {
+        if (ms) {
+            ms[i] = ctx->kernel_ms[i];
+        }
+        if (launches) {
+            launches[i] = ctx->kernel_launches[i];
+        }
+    }
+    return 0;
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------------------------
+int rc_stage_generate_primary_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays_out, void *hits_out,
+                                   int *count_out) {
+    if (!ctx || !pass || !rays_out || !hits_out || !count_out) {
+        return fail(ctx, "rc_stage_generate_primary_rays: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    KParams p;
+    if (fill_params(ctx, pass, p)) {
+        return 1;
+    }
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), ctx->stream));
+    const int n_pix_tiles = ((p.rect_w + 7) / 8) * ((p.rect_h + 3) / 4);
+    k_raygen<<<(n_pix_tiles * 32 + 255) / 256, 256, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t n = 0;
+    if (get_counter(ctx, CNT_RAYS + 0, &n)) {
+        return 1;
+    }
+    *count_out = int(n);
+    if (n) {
+        if (download_rays_aos(ctx, ctx->rays[0], static_cast<RayAoS *>(rays_out), int(n)) ||
+            download_hits_aos(ctx, ctx->hits, static_cast<HitAoS *>(hits_out), int(n))) {
+            return 1;
+        }
+    }
+    return 0;
+}
+
+int rc_stage_trace_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays, void *hits, int count, int trace_lights) {
+    if (!ctx || !pass || !rays || !hits || count < 0) {
+        return fail(ctx, "rc_stage_trace_rays: bad argument");
+    }
+    cudaSetDevice(ctx->device);
+    if (size_t(count) > ctx->ray_capacity) {
+        return fail(ctx, "rc_stage_trace_rays: %d rays exceed the capacity %zu (w*h)", count, ctx->ray_capacity);
+    }
+    KParams p;
+    if (fill_params(ctx, pass, p)) {
+        return 1;
+    }
+    if (count == 0) {
+        return 0;
+    }
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (upload_rays_aos(ctx, ctx->rays[0], static_cast<const RayAoS *>(rays), count) ||
+        upload_hits_aos(ctx, ctx->hits, static_cast<const HitAoS *>(hits), count) ||
+        set_counter(ctx, CNT_RAYS + 0, uint32_t(count))) {
+        return 1;
+    }
+    const int grid = persistent_grid(ctx, 8);
+    if (ctx->scene_info.tlas_root != 0xffffffffu) {
+        if (trace_lights && ctx->scene_info.visible_lights_count != 0) {
+            k_trace_closest<true, false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0);
+        } else {
+            k_trace_closest<false, false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0);
+        }
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    return download_rays_aos(ctx, ctx->rays[0], static_cast<RayAoS *>(rays), count) ||
+           download_hits_aos(ctx, ctx->hits, static_cast<HitAoS *>(hits), count);
+}
+
+int rc_stage_shade(rc_ctx *ctx, const rc_pass_desc *pass, int primary, int bounce, const void *rays, const void *hits,
+                   int count, void *secondary_out, int *secondary_count, void *shadow_out, int *shadow_count) {
+    if (!ctx || !pass || !rays || !hits || count < 0 || !secondary_out || !secondary_count || !shadow_out ||
+        !shadow_count) {
+        return fail(ctx, "rc_stage_shade: bad argument");
+    }
+    cudaSetDevice(ctx->device);
+    if (size_t(count) > ctx->ray_capacity) {
+        return fail(ctx, "rc_stage_shade: %d rays exceed the capacity %zu (w*h)", count, ctx->ray_capacity);
+    }
+    KParams p;
+    if (fill_params(ctx, pass, p)) {
+        return 1;
+    }
+    *secondary_count = *shadow_count = 0;
+    if (count == 0) {
+        return 0;
+    }
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (upload_rays_aos(ctx, ctx->rays[0], static_cast<const RayAoS *>(rays), count) ||
+        upload_hits_aos(ctx, ctx->hits, static_cast<const HitAoS *>(hits), count) ||
+        set_counter(ctx, CNT_RAYS + 0, uint32_t(count))) {
+        return 1;
+    }
+    const int grid = persistent_grid(ctx, 4);
+    const float mix_factor = 1.0f / float(p.iteration);
+    if (primary) {
+        const float lim = clamp_limit(p.ps.clamp_direct);
+        k_shade<true><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
+                                                      mix_factor);
+    } else {
+        const float cd = (bounce == 1) ? p.ps.clamp_direct : p.ps.clamp_indirect;
+        k_shade<false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0,
+                                                       clamp_limit(cd), clamp_limit(p.ps.clamp_indirect), mix_factor);
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    uint32_t ns = 0, nh = 0;
+    if (get_counter(ctx, CNT_RAYS + 1, &ns) || get_counter(ctx, CNT_SHADOW + 0, &nh)) {
+        return 1;
+    }
+    *secondary_count = int(ns);
+    *shadow_count = int(nh);
+    if (ns && download_rays_aos(ctx, ctx->rays[1], static_cast<RayAoS *>(secondary_out), int(ns))) {
+        return 1;
+    }
+    if (nh && download_shadow_aos(ctx, ctx->shadow, static_cast<ShadowRayAoS *>(shadow_out), int(nh))) {
+        return 1;
+    }
+    return 0;
+}
+
+int rc_stage_trace_shadow_rays(rc_ctx *ctx, const rc_pass_desc *pass, const void *shadow_rays, int count,
+                               float clamp_val) {
+    if (!ctx || !pass || !shadow_rays || count < 0) {
+        return fail(ctx, "rc_stage_trace_shadow_rays: bad argument");
+    }
+    cudaSetDevice(ctx->device);
+    if (size_t(count) > ctx->ray_capacity) {
+        return fail(ctx, "rc_stage_trace_shadow_rays: %d rays exceed the capacity %zu", count, ctx->ray_capacity);
+    }
+    KParams p;
+    if (fill_params(ctx, pass, p)) {
+        return 1;
+    }
+    if (count == 0) {
+        return 0;
+    }
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (upload_shadow_aos(ctx, ctx->shadow, static_cast<const ShadowRayAoS *>(shadow_rays), count) ||
+        set_counter(ctx, CNT_SHADOW + 0, uint32_t(count))) {
+        return 1;
+    }
+    if (ctx->scene_info.tlas_root != 0xffffffffu) {
+        k_trace_shadow<<<persistent_grid(ctx, 8), 128, 0, ctx->stream>>>(p, ctx->shadow, 0, clamp_limit(clamp_val));
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int rc_stage_sort_rays(rc_ctx *ctx, void *rays, int count, uint32_t *hashes_out) {
+    if (!ctx || !rays || count < 0) {
+        return fail(ctx, "rc_stage_sort_rays: bad argument");
+    }
+    cudaSetDevice(ctx->device);
+    if (size_t(count) > ctx->ray_capacity) {
+        return fail(ctx, "rc_stage_sort_rays: %d rays exceed the capacity %zu", count, ctx->ray_capacity);
+    }
+    if (!ctx->have_scene) {
+        return fail(ctx, "no scene uploaded");
+    }
+    if (count == 0) {
+        return 0;
+    }
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.counters = ctx->d_counters;
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (upload_rays_aos(ctx, ctx->rays[0], static_cast<const RayAoS *>(rays), count) ||
+        set_counter(ctx, CNT_RAYS + 1, uint32_t(count))) {
+        return 1;
+    }
+    sort_rays(ctx->sort, p, ctx->rays[0], ctx->rays[1], 1, ctx->num_sms, ctx->stream);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    if (download_rays_aos(ctx, ctx->rays[1], static_cast<RayAoS *>(rays), count)) {
+        return 1;
+    }
+    if (hashes_out) {
+        CU_CHECK(ctx, cudaMemcpy(hashes_out, ctx->sort.keys_sorted, size_t(count) * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,340 @@
+// rt_math.cuh -- scalar float math with the reference's exact operation order.
+//
+// Parity with Ref (reference internal/CoreRef.cpp, ShadeRef.cpp) needs every rounding to happen where the reference's
+// SSE2 build puts it: the TU is compiled with -msse2 -mno-avx (reference CMakeLists.txt:41), i.e. no fma contraction,
+// IEEE div/sqrt; this TU is compiled with -fmad=false and default (IEEE) division and square root.  Vector helpers
+// reproduce the association order of the reference's 4-wide `fvec4` reductions (internal/simd/simd_sse.h):
+//   dot/length : (x*x' + y*y') + (w*w' + z*z')            simd_sse.h:120-142, 252-260
+//   hsum       : ((x + y) + z) + w                        simd_sse.h:144-152 (no SSE4.1 in the Ref TU)
+//   min/max    : _mm_min_ps / _mm_max_ps operand order    simd_sse.h:180-188
+// v3 is an fvec4 whose 4th lane is known to be 0, so w*w' + z*z' == z*z'.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_types.h"
+
+#define RT_DEV __device__ __forceinline__
+
+namespace rt {
+
+struct v2 {
+    float x, y;
+};
+struct v3 {
+    float x, y, z;
+};
+struct v4 {
+    float x, y, z, w;
+};
+
+RT_DEV v3 mk3(float x, float y, float z) { return v3{x, y, z}; }
+RT_DEV v3 mk3(const float *p) { return v3{p[0], p[1], p[2]}; }
+RT_DEV v2 mk2(float x, float y) { return v2{x, y}; }
+
+RT_DEV v3 operator+(v3 a, v3 b) { return v3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+RT_DEV v3 operator-(v3 a, v3 b) { return v3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+RT_DEV v3 operator*(v3 a, v3 b) { return v3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+RT_DEV v3 operator/(v3 a, v3 b) { return v3{a.x / b.x, a.y / b.y, a.z / b.z}; }
+RT_DEV v3 operator*(v3 a, float s) { return v3{a.x * s, a.y * s, a.z * s}; }
+RT_DEV v3 operator*(float s, v3 a) { return v3{s * a.x, s * a.y, s * a.z}; }
+RT_DEV v3 operator/(v3 a, float s) { return v3{a.x / s, a.y / s, a.z / s}; }
+RT_DEV v3 operator-(v3 a) { return v3{-a.x, -a.y, -a.z}; }
+RT_DEV v3 &operator+=(v3 &a, v3 b) {
+    a = a + b;
+    return a;
+}
+RT_DEV v3 &operator*=(v3 &a, v3 b) {
+    a = a * b;
+    return a;
+}
+RT_DEV v3 &operator*=(v3 &a, float s) {
+    a = a * s;
+    return a;
+}
+RT_DEV v3 &operator/=(v3 &a, float s) {
+    a = a / s;
+    return a;
+}
+
+RT_DEV v2 operator+(v2 a, v2 b) { return v2{a.x + b.x, a.y + b.y}; }
+RT_DEV v2 operator-(v2 a, v2 b) { return v2{a.x - b.x, a.y - b.y}; }
+RT_DEV v2 operator*(v2 a, v2 b) { return v2{a.x * b.x, a.y * b.y}; }
+RT_DEV v2 operator*(v2 a, float s) { return v2{a.x * s, a.y * s}; }
+RT_DEV v2 operator*(float s, v2 a) { return v2{s * a.x, s * a.y}; }
+
+// simd_sse.h:252-260 with the w lane zero.
+RT_DEV float dot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z); }
+RT_DEV float length(v3 a) { return sqrtf(dot(a, a)); }
+RT_DEV float length2(v3 a) { return dot(a, a); }
+RT_DEV v3 normalize(v3 a) { return a / length(a); }
+RT_DEV v3 normalize_len(v3 a, float &len) {
+    len = length(a);
+    return a / len;
+}
+// generic fvec<2>: accumulates left to right from 0 (simd.h:304-314,475-479)
+RT_DEV float dot(v2 a, v2 b) { return (0.0f + a.x * b.x) + a.y * b.y; }
+RT_DEV float length(v2 a) { return sqrtf(dot(a, a)); }
+
+// CoreRef.h:281-285
+RT_DEV v3 cross(v3 a, v3 b) { return v3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// _mm_min_ps(a,b) = a < b ? a : b ; _mm_max_ps(a,b) = a > b ? a : b  (second operand on NaN / equal)
+RT_DEV float sse_min(float a, float b) { return a < b ? a : b; }
+RT_DEV float sse_max(float a, float b) { return a > b ? a : b; }
+// std::min / std::max as used by the generic fvec<2> (simd.h:388-398)
+RT_DEV float std_min(float a, float b) { return (b < a) ? b : a; }
+RT_DEV float std_max(float a, float b) { return (a < b) ? b : a; }
+
+RT_DEV float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); } // Core.h:537-539
+RT_DEV float saturatef(float v) { return clampf(v, 0.0f, 1.0f); }
+RT_DEV float sqr(float x) { return x * x; }
+RT_DEV float mixf(float a, float b, float k) { return (1.0f - k) * a + k * b; } // ShadeRef.cpp:30
+RT_DEV v3 mix3(v3 a, v3 b, float k) { return (1.0f - k) * a + k * b; }          // simd.h:609-611
+RT_DEV float fractf(float v) { return v - floorf(v); }                          // CoreRef.h:158
+
+RT_DEV float safe_sqrt(float v) { return sqrtf(fmaxf(v, 0.0f)); }
+RT_DEV float safe_div(float a, float b) { return b != 0.0f ? (a / b) : kFltMax; }
+RT_DEV float safe_div_pos(float a, float b) { return a / fmaxf(b, kFltEps); }
+RT_DEV float safe_div_neg(float a, float b) { return a / fminf(b, -kFltEps); }
+RT_DEV v3 safe_normalize(v3 a) {
+    const float l = length(a);
+    return l > 0.0f ? (a / l) : a;
+}
+// CoreRef.h:193-197
+RT_DEV v3 safe_invert(v3 d) {
+    v3 r;
+    r.x = 1.0f / ((fabsf(d.x) > kFltEps) ? d.x : copysignf(kFltEps, d.x));
+    r.y = 1.0f / ((fabsf(d.y) > kFltEps) ? d.y : copysignf(kFltEps, d.y));
+    r.z = 1.0f / ((fabsf(d.z) > kFltEps) ? d.z : copysignf(kFltEps, d.z));
+    return r;
+}
+
+RT_DEV float lum(v3 c) { return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z; } // CoreRef.h:398-404
+RT_DEV float power_heuristic(float a, float b) {                                         // CoreRef.h:424-427
+    const float t = a * a;
+    return t / (b * b + t);
+}
+
+RT_DEV float fast_log2(float val) { // CoreRef.h:406-417
+    int x = __float_as_int(val);
+    float log_2 = float(((x >> 23) & 255) - 128);
+    x &= ~(255 << 23);
+    x += 127 << 23;
+    const float m = __int_as_float(x);
+    log_2 += ((-0.34484843f) * m + 2.02466578f) * m - 0.67487759f;
+    return log_2;
+}
+
+// "A Fast and Robust Method for Avoiding Self-Intersection" as in CoreRef.h:447-462 (ivec4(float) truncates).
+RT_DEV v3 offset_ray(v3 p, v3 n) {
+    const float Origin = 1.0f / 32.0f;
+    const float FloatScale = 1.0f / 65536.0f;
+    const float IntScale = 128.0f;
+    const int ox = __float2int_rz(IntScale * n.x), oy = __float2int_rz(IntScale * n.y),
+              oz = __float2int_rz(IntScale * n.z);
+    const float ix = __int_as_float(__float_as_int(p.x) + ((p.x < 0.0f) ? -ox : ox));
+    const float iy = __int_as_float(__float_as_int(p.y) + ((p.y < 0.0f) ? -oy : oy));
+    const float iz = __int_as_float(__float_as_int(p.z) + ((p.z < 0.0f) ? -oz : oz));
+    return v3{fabsf(p.x) < Origin ? (p.x + FloatScale * n.x) : ix, fabsf(p.y) < Origin ? (p.y + FloatScale * n.y) : iy,
+              fabsf(p.z) < Origin ? (p.z + FloatScale * n.z) : iz};
+}
+
+// ---- trigonometry: the reference's own polynomials (CoreRef.cpp:1131-1270), not CUDA's --------------------------
+// portable_cos/sin evaluate three range-shifted copies of one polynomial and select with a 0/1 mask through a dot
+// product; exactly one mask lane is +-1 and the others are 0, so evaluating only the selected lane is bit-identical.
+RT_DEV float trig_poly(float arg) {
+    arg = arg * arg;
+    float res = -25.0407296503853054f * arg + 60.1524123580209817f;
+    res = res * arg - 85.4539888046442542f;
+    res = res * arg + 64.9393549651994562f;
+    res = res * arg - 19.7392086060579359f;
+    res = res * arg + 0.9999999998415476f;
+    return res;
+}
+RT_DEV float trig_select(float a) { // a in [0,1): fraction of a full turn
+    if (a < 0.25f) {
+        return trig_poly(a);
+    } else if (a >= 0.75f) {
+        return trig_poly(a - 1.0f);
+    }
+    return -trig_poly(a - 0.5f);
+}
+RT_DEV float portable_cos(float a) { return trig_select(fractf(fabsf(a) * 0.15915494309189535f)); }
+RT_DEV float portable_sin(float a) {
+    return trig_select(fractf(fabsf(a - 1.5707963267948966f) * 0.15915494309189535f));
+}
+// returns {sin, cos} like Ref::portable_sincos
+RT_DEV v2 portable_sincos(float a) { return v2{portable_sin(a), portable_cos(a)}; }
+
+RT_DEV float asin_tail(float x) {
+    return (kPi / 2) - ((x + 2.71745038f) * x + 14.0375338f) * (0.00440413551f * ((x - 8.31223679f) * x + 25.3978882f)) *
+                           sqrtf(1 - x);
+}
+RT_DEV float portable_asinf(float x) {
+    if (fabsf(x) > 0.57f) {
+        const float ret = asin_tail(fabsf(x));
+        return (x < 0.0f) ? -ret : ret;
+    } else {
+        const float x2 = x * x;
+        return x + (0.0517513789f * ((x2 + 1.83372748f) * x2 + 1.56678128f)) * x *
+                       (x2 * ((x2 - 1.48268414f) * x2 + 2.05554748f));
+    }
+}
+RT_DEV float portable_acosf(float x) {
+    if (x < -0.62f) {
+        return kPi - (((x - 2.71850395f) * x + 14.7303705f)) * (0.00393401226f * ((x + 8.60734272f) * x + 27.0927486f)) *
+                         sqrtf(1 + x);
+    } else if (x <= 0.62f) {
+        const float x2 = x * x;
+        return (kPi / 2) - x -
+               (0.0700945929f * x * ((x2 + 1.57144082f) * x2 + 1.25210774f)) *
+                   (x2 * ((x2 - 1.53757966f) * x2 + 1.89929986f));
+    } else {
+        return (((x + 2.71850395f) * x + 14.7303705f)) * (0.00393401226f * ((x - 8.60734272f) * x + 27.0927486f)) *
+               sqrtf(1 - x);
+    }
+}
+
+// acosf as glibc 2.39 computes it for binary32 (sysdeps/ieee754/flt-32/e_acosf.c, the fdlibm algorithm in float
+// arithmetic).  The reference calls libm acosf in slerp() (CoreRef.cpp:1110-1126) and for spot lights; CUDA's acosf
+// is a different <=1-ulp approximation, and one ulp in a sampled direction is enough to flip a later discrete
+// decision.  tests/test_libm.py checks this restatement against the host libm over the whole [-1,1] domain.
+RT_DEV float libm_acosf(float x) {
+    const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f,
+                pio2_lo = 7.5497894159e-08f, pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f,
+                pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f, pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f,
+                qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f, qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+    const int hx = __float_as_int(x);
+    const int ix = hx & 0x7fffffff;
+    if (ix == 0x3f800000) {
+        if (hx > 0) {
+            return 0.0f;
+        }
+        return pi + 2.0f * pio2_lo;
+    } else if (ix > 0x3f800000) {
+        return (x - x) / (x - x);
+    }
+    if (ix < 0x3f000000) { // |x| < 0.5
+        if (ix <= 0x23000000) {
+            return pio2_hi + pio2_lo;
+        }
+        const float z = x * x;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    } else if (hx < 0) { // x < -0.5
+        const float z = (one + x) * 0.5f;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float s = sqrtf(z);
+        const float r = p / q;
+        const float w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    } else { // x > 0.5
+        const float z = (one - x) * 0.5f;
+        const float s = sqrtf(z);
+        const float df = __int_as_float(__float_as_int(s) & 0xfffff000);
+        const float c = (z - df * df) / (s + df);
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float r = p / q;
+        const float w = r * s + c;
+        return 2.0f * (df + w);
+    }
+}
+
+// CoreRef.cpp:771-802
+RT_DEV float approx_atan2(float y, float x) {
+    float t0, t1, t3, t4;
+    t3 = fabsf(x);
+    t1 = fabsf(y);
+    t0 = fmaxf(t3, t1);
+    t1 = fminf(t3, t1);
+    t3 = 1.0f / t0;
+    t3 = t1 * t3;
+    t4 = t3 * t3;
+    t0 = -0.013480470f;
+    t0 = t0 * t4 + 0.057477314f;
+    t0 = t0 * t4 - 0.121239071f;
+    t0 = t0 * t4 + 0.195635925f;
+    t0 = t0 * t4 - 0.332994597f;
+    t0 = t0 * t4 + 0.999995630f;
+    t3 = t0 * t3;
+    t3 = (fabsf(y) > fabsf(x)) ? 1.570796327f - t3 : t3;
+    t3 = (x < 0) ? 3.141592654f - t3 : t3;
+    t3 = (y < 0) ? -t3 : t3;
+    return t3;
+}
+
+// ---- matrices (column-major 4x4), CoreRef.cpp:2789-2816 -----------------------------------------------------------
+RT_DEV v3 transform_point(v3 p, const float *m) {
+    return v3{m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+              m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]};
+}
+RT_DEV v3 transform_direction(v3 p, const float *m) {
+    return v3{m[0] * p.x + m[4] * p.y + m[8] * p.z, m[1] * p.x + m[5] * p.y + m[9] * p.z,
+              m[2] * p.x + m[6] * p.y + m[10] * p.z};
+}
+RT_DEV v3 transform_normal(v3 n, const float *inv) {
+    return v3{inv[0] * n.x + inv[1] * n.y + inv[2] * n.z, inv[4] * n.x + inv[5] * n.y + inv[6] * n.z,
+              inv[8] * n.x + inv[9] * n.y + inv[10] * n.z};
+}
+
+RT_DEV v3 world_from_tangent(v3 T, v3 B, v3 N, v3 V) { return V.x * T + V.y * B + V.z * N; } // CoreRef.h:296-298
+RT_DEV v3 tangent_from_world(v3 T, v3 B, v3 N, v3 V) { return v3{dot(V, T), dot(V, B), dot(V, N)}; }
+
+// CoreRef.cpp:675-688
+RT_DEV void create_tbn(v3 N, v3 &T, v3 &B) {
+    v3 U;
+    if (fabsf(N.y) < 0.999f) {
+        U = v3{0.0f, 1.0f, 0.0f};
+    } else {
+        U = v3{1.0f, 0.0f, 0.0f};
+    }
+    T = normalize(cross(U, N));
+    B = cross(N, T);
+}
+
+// ---- ray depth packing, CoreRef.h:253-280 --------------------------------------------------------------------------
+RT_DEV int diff_depth(uint32_t d) { return int(d & 0x7f); }
+RT_DEV int spec_depth(uint32_t d) { return int(d >> 7) & 0x7f; }
+RT_DEV int refr_depth(uint32_t d) { return int(d >> 14) & 0x7f; }
+RT_DEV int transp_depth(uint32_t d) { return int(d >> 21) & 0x7f; }
+RT_DEV int total_depth(uint32_t d) { return diff_depth(d) + spec_depth(d) + refr_depth(d) + transp_depth(d); }
+RT_DEV int ray_type(uint32_t d) { return int(d >> 28) & 0xf; }
+RT_DEV bool is_indirect(uint32_t d) { return (d & 0x001fffff) != 0; }
+RT_DEV uint32_t pack_depth(int diff, int spec, int refr, int transp) {
+    return uint32_t(diff) | (uint32_t(spec) << 7) | (uint32_t(refr) << 14) | (uint32_t(transp) << 21);
+}
+
+// ---- sampler: Owen-scrambled lookup into the PMJ02 table, CoreRef.cpp:1068-1101, 1418-1427 -------------------------
+RT_DEV uint32_t hash_u32(uint32_t x) { // CoreRef.h:133-141
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+RT_DEV uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+RT_DEV uint32_t laine_karras(uint32_t x, uint32_t seed) {
+    x += seed;
+    x ^= x * 0x6c50b47cu;
+    x ^= x * 0xb82f1e52u;
+    x ^= x * 0xc7afe638u;
+    x ^= x * 0x8d22f6e6u;
+    return x;
+}
+RT_DEV uint32_t owen_scramble(uint32_t x, uint32_t seed) { return __brev(laine_karras(__brev(x), seed)); }
+RT_DEV float scramble_unorm(uint32_t seed, uint32_t val) { return float(owen_scramble(val, seed) >> 8) / 16777216.0f; }
+RT_DEV v2 rand2d(uint32_t dim, uint32_t seed, int sample, const uint32_t *__restrict__ seq) {
+    const uint32_t sd = owen_scramble(dim, seed) & (kRandDims - 1);
+    const uint32_t si = owen_scramble(uint32_t(sample), hash_combine(seed, dim)) & (kRandSamples - 1);
+    const uint2 s = __ldg(reinterpret_cast<const uint2 *>(seq + sd * 2 * kRandSamples + 2 * si));
+    return v2{scramble_unorm(hash_combine(seed, 2 * dim + 0), s.x), scramble_unorm(hash_combine(seed, 2 * dim + 1), s.y)};
+}
+
+} // namespace rt
