@@ -155,8 +155,11 @@ int rc_stage_trace_shadow_rays(rc_ctx *ctx, const rc_pass_desc *pass, const void
                                float clamp_val);
 /* results-neutral: reorders rays in place by the reference's ray hash; returns the hash of each output ray */
 int rc_stage_sort_rays(rc_ctx *ctx, void *rays, int count, uint32_t *hashes_out);
-/* overwrite a rect of the TEMP buffer (stage tests) */
+/* overwrite the TEMP buffer (stage tests) */
 int rc_debug_fill_temp(rc_ctx *ctx, const float rgba[4]);
+/* sizeof() of the ABI structs as compiled into the library: 0 rc_array, 1 rc_scene_view, 2 rc_camera, 3 rc_rect,
+ * 4 rc_pass_desc, 5 rc_counters; -1 for an unknown id.  Lets a binding verify its struct mirrors. */
+int rc_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }

@@ -1109,4 +1109,16 @@ int rc_stage_sort_rays(rc_ctx *ctx, void *rays, int count, uint32_t *hashes_out)
     return 0;
 }
 
+int rc_abi_sizeof(int which) {
+    switch (which) {
+    case 0: return int(sizeof(rc_array));
+    case 1: return int(sizeof(rc_scene_view));
+    case 2: return int(sizeof(rc_camera));
+    case 3: return int(sizeof(rc_rect));
+    case 4: return int(sizeof(rc_pass_desc));
+    case 5: return int(sizeof(rc_counters));
+    default: return -1;
+    }
+}
+
 } // extern "C"
