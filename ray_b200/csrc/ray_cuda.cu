@@ -761,9 +761,11 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
             if (m[i].type > NODE_PRINCIPLED) {
                 continue;
             }
-            const bool is_mix = (m[i].type == NODE_MIX);
-            for (int t = 0; t < 5; ++t) {
-                if (is_mix && (t == kMixMat1 || t == kMixMat2)) {
+            // only the slots ShadeSurface reads for this node type are meaningful: AddMaterial zero-initialises
+            // material_t and leaves the others at 0 (SceneCPU.cpp:208-247); Mix keeps child ids in slots 3/4
+            const int n_slots = (m[i].type == NODE_PRINCIPLED) ? 5 : 3;
+            for (int t = 0; t < n_slots; ++t) {
+                if (m[i].type == NODE_MIX && t != kTexBase) {
                     continue;
                 }
                 if (m[i].textures[t] != 0xffffffffu) {
