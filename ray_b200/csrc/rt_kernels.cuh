@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(KParams p, RayBuf rays, H
 // ---- ShadePrimary / ShadeSecondary (ShadeRef.cpp:1654-1737) --------------------------------------------------------
 // `bounce` = index of the ray list being shaded (0 = primary).  Secondary rays go to list bounce+1.
 template <bool PRIMARY>
-__global__ void __launch_bounds__(128) k_shade(KParams p, RayBuf rays, HitBuf hits, RayBuf out_rays, ShadowBuf out_shadow,
+__global__ void __launch_bounds__(128, 4) k_shade(KParams p, RayBuf rays, HitBuf hits, RayBuf out_rays, ShadowBuf out_shadow,
                                                int bounce, float limit0, float limit1, float mix_factor) {
     const uint32_t count = p.counters[CNT_RAYS + bounce];
     const int lane = threadIdx.x & 31;

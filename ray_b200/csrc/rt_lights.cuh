@@ -38,10 +38,10 @@ struct SceneLights {
 };
 
 // Unpack the 8 quantised child boxes of a light-tree node into [3][8] arrays.
-RT_DEV void unpack_cw_bounds(const LightCWNode &n, float bmin[24], float bmax[24]) {
+RT_FN void unpack_cw_bounds(const LightCWNode &n, float bmin[24], float bmax[24]) {
     const float ext0 = (n.bbox_max[0] - n.bbox_min[0]) / 255.0f, ext1 = (n.bbox_max[1] - n.bbox_min[1]) / 255.0f,
                 ext2 = (n.bbox_max[2] - n.bbox_min[2]) / 255.0f;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; ++i) {
         bmin[0 * 8 + i] = bmin[1 * 8 + i] = bmin[2 * 8 + i] = -kMaxDist;
         bmax[0 * 8 + i] = bmax[1 * 8 + i] = bmax[2 * 8 + i] = kMaxDist;
@@ -60,11 +60,13 @@ RT_DEV float sse_abs(float v) { return sse_max(v, -v); } // abs(fvec4) = max(v, 
 
 // calc_lnode_importance for the quantised node, one child lane at a time (the reference works on 4 lanes at once; all
 // operations are lane-wise, so the per-lane result is identical).
-RT_DEV void lnode_importance(const LightCWNode &n, const float bmin[24], const float bmax[24], v3 P, float imp[8]) {
-#pragma unroll
+RT_FN void lnode_importance(const LightCWNode &n, const float bmin[24], const float bmax[24], v3 P, float imp[8]) {
+#pragma unroll 1
     for (int i = 0; i < 8; ++i) {
         float v = n.flux[i];
-        if (bmin[0 * 8 + i] > -kMaxDist) {
+        // A zero-flux lane (empty slot, Core.cpp:1176-1183) can only produce +-0 below (flux * mul with a finite or
+        // zeroed mul), and +-0 behaves identically in every sum, quotient and comparison downstream: skip the math.
+        if (v != 0.0f && bmin[0 * 8 + i] > -kMaxDist) {
             // decode_oct_dir (vector form)
             const uint32_t oct = n.axis[i];
             float a0 = -1.0f + 2.0f * float((oct >> 16) & 0xffffu) / 65535.0f;
@@ -134,7 +136,7 @@ RT_DEV float sum_importance(const float imp[8]) {
     return (imp[0] + imp[4]) + (imp[1] + imp[5]) + (imp[2] + imp[6]) + (imp[3] + imp[7]);
 }
 
-RT_DEV v3 map_to_cone(float r1, float r2, v3 N, float radius) {
+RT_FN v3 map_to_cone(float r1, float r2, v3 N, float radius) {
     const float ox = 2.0f * r1 - 1.0f, oy = 2.0f * r2 - 1.0f;
     if (ox == 0.0f && oy == 0.0f) {
         return N;
@@ -180,9 +182,9 @@ RT_DEV bool quadratic(float a, float b, float c, float &t0, float &t1) {
     return true;
 }
 
-RT_DEV v3 orthogonalize(v3 a, v3 b) { return normalize(b - dot(a, b) * a); }
+RT_FN v3 orthogonalize(v3 a, v3 b) { return normalize(b - dot(a, b) * a); }
 
-RT_DEV v3 slerp(v3 start, v3 end, float percent) {
+RT_FN v3 slerp(v3 start, v3 end, float percent) {
     float cos_theta = dot(start, end);
     cos_theta = clampf(cos_theta, -1.0f, 1.0f);
     const float theta = libm_acosf(cos_theta) * percent;
@@ -191,7 +193,7 @@ RT_DEV v3 slerp(v3 start, v3 end, float percent) {
     return start * sc.y + relative_vec * sc.x;
 }
 
-RT_DEV float angle_between(v3 v1, v3 v2) {
+RT_FN float angle_between(v3 v1, v3 v2) {
     if (dot(v1, v2) < 0) {
         return kPi - 2 * portable_asinf(length(v1 + v2) / 2);
     } else {
@@ -200,7 +202,7 @@ RT_DEV float angle_between(v3 v1, v3 v2) {
 }
 
 // Returns pdf (1/solid angle) or 0; writes the sampled point when out_p != nullptr.
-RT_DEV float sample_spherical_rectangle(v3 P, v3 light_pos, v3 axis_u, v3 axis_v, v2 Xi, v3 *out_p) {
+RT_FN float sample_spherical_rectangle(v3 P, v3 light_pos, v3 axis_u, v3 axis_v, v2 Xi, v3 *out_p) {
     const v3 corner = light_pos - 0.5f * axis_u - 0.5f * axis_v;
     float axisu_len, axisv_len;
     const v3 x = normalize_len(axis_u, axisu_len), y = normalize_len(axis_v, axisv_len);
@@ -257,7 +259,7 @@ RT_DEV float sample_spherical_rectangle(v3 P, v3 light_pos, v3 axis_u, v3 axis_v
     return (1.0f / area);
 }
 
-RT_DEV float sample_spherical_triangle(v3 P, v3 p1, v3 p2, v3 p3, v2 Xi, v3 *out_dir) {
+RT_FN float sample_spherical_triangle(v3 P, v3 p1, v3 p2, v3 p3, v2 Xi, v3 *out_dir) {
     const v3 A = normalize(p1 - P), B = normalize(p2 - P), C = normalize(p3 - P);
     const v3 BA = orthogonalize(A, B - A);
     const v3 CA = orthogonalize(A, C - A);
@@ -301,7 +303,7 @@ struct SceneSurf { // the arrays shading needs besides SceneGeo
 
 // SampleLightSource with hierarchical NEE (USE_HIERARCHICAL_NEE, USE_SPHERICAL_AREA_LIGHT_SAMPLING = true).
 // Textured lights / env maps are not supported by this backend (rc_upload_scene rejects them).
-RT_DEV void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, const SceneGeo &sg, const SceneSurf &ss,
+RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, const SceneGeo &sg, const SceneSurf &ss,
                                 float rand_pick_light, v2 rand_light_uv, LightSample &ls) {
     float u1 = rand_pick_light;
     float factor = 1.0f;
@@ -560,7 +562,7 @@ RT_DEV void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, c
 }
 
 // IntersectAreaLights for one ray (secondary rays): analytic lights through the light tree, tracking the pdf factor.
-RT_DEV void intersect_area_lights(const SceneLights &sl, v3 ro, v3 rd, uint32_t ray_flags, Hit &inter,
+RT_FN void intersect_area_lights(const SceneLights &sl, v3 ro, v3 rd, uint32_t ray_flags, Hit &inter,
                                   LightStackEntry *st) {
     const v3 inv_d = safe_invert(rd);
     int sp = 0;
@@ -771,7 +773,7 @@ RT_DEV void intersect_area_lights(const SceneLights &sl, v3 ro, v3 rd, uint32_t 
 }
 
 // Blocker lights for shadow rays: returns 0 when a rect/disk light blocks the ray, 1 otherwise.
-RT_DEV float intersect_area_lights_shadow(const SceneLights &sl, v3 ro, v3 rd, float ray_dist, StackEntry *st) {
+RT_FN float intersect_area_lights_shadow(const SceneLights &sl, v3 ro, v3 rd, float ray_dist, StackEntry *st) {
     const float rdist = fabsf(ray_dist);
     const v3 inv_d = safe_invert(rd);
     int sp = 0;
@@ -898,7 +900,7 @@ RT_DEV uint32_t point_in_box8(const float bmin[24], const float bmax[24], v3 p) 
 }
 
 // EvalTriLightFactor: probability factor with which NEE would have picked emissive triangle `tri_index` from `ro`.
-RT_DEV float eval_tri_light_factor(const SceneLights &sl, v3 P, v3 ro, uint32_t tri_index, uint32_t *stack,
+RT_FN float eval_tri_light_factor(const SceneLights &sl, v3 P, v3 ro, uint32_t tri_index, uint32_t *stack,
                                    float *stack_factors) {
     int sp = 0;
     stack_factors[sp] = 1.0f;

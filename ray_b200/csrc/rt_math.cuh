@@ -16,6 +16,9 @@
 #include "rt_types.h"
 
 #define RT_DEV __device__ __forceinline__
+// Heavy leaf functions are real calls: the shade kernel was 460 KB of SASS when everything was inlined and stalled on
+// instruction fetch (ncu: no_instruction 1.6-4.0 stalls per issue).  Inlining never changes results here (-fmad=false).
+#define RT_FN __device__ __noinline__
 
 namespace rt {
 
@@ -68,8 +71,8 @@ RT_DEV v2 operator*(float s, v2 a) { return v2{s * a.x, s * a.y}; }
 RT_DEV float dot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z); }
 RT_DEV float length(v3 a) { return sqrtf(dot(a, a)); }
 RT_DEV float length2(v3 a) { return dot(a, a); }
-RT_DEV v3 normalize(v3 a) { return a / length(a); }
-RT_DEV v3 normalize_len(v3 a, float &len) {
+RT_FN v3 normalize(v3 a) { return a / length(a); }
+RT_FN v3 normalize_len(v3 a, float &len) {
     len = length(a);
     return a / len;
 }
@@ -98,12 +101,12 @@ RT_DEV float safe_sqrt(float v) { return sqrtf(fmaxf(v, 0.0f)); }
 RT_DEV float safe_div(float a, float b) { return b != 0.0f ? (a / b) : kFltMax; }
 RT_DEV float safe_div_pos(float a, float b) { return a / fmaxf(b, kFltEps); }
 RT_DEV float safe_div_neg(float a, float b) { return a / fminf(b, -kFltEps); }
-RT_DEV v3 safe_normalize(v3 a) {
+RT_FN v3 safe_normalize(v3 a) {
     const float l = length(a);
     return l > 0.0f ? (a / l) : a;
 }
 // CoreRef.h:193-197
-RT_DEV v3 safe_invert(v3 d) {
+RT_FN v3 safe_invert(v3 d) {
     v3 r;
     r.x = 1.0f / ((fabsf(d.x) > kFltEps) ? d.x : copysignf(kFltEps, d.x));
     r.y = 1.0f / ((fabsf(d.y) > kFltEps) ? d.y : copysignf(kFltEps, d.y));
@@ -128,7 +131,7 @@ RT_DEV float fast_log2(float val) { // CoreRef.h:406-417
 }
 
 // "A Fast and Robust Method for Avoiding Self-Intersection" as in CoreRef.h:447-462 (ivec4(float) truncates).
-RT_DEV v3 offset_ray(v3 p, v3 n) {
+RT_FN v3 offset_ray(v3 p, v3 n) {
     const float Origin = 1.0f / 32.0f;
     const float FloatScale = 1.0f / 65536.0f;
     const float IntScale = 128.0f;
@@ -161,18 +164,18 @@ RT_DEV float trig_select(float a) { // a in [0,1): fraction of a full turn
     }
     return -trig_poly(a - 0.5f);
 }
-RT_DEV float portable_cos(float a) { return trig_select(fractf(fabsf(a) * 0.15915494309189535f)); }
-RT_DEV float portable_sin(float a) {
+RT_FN float portable_cos(float a) { return trig_select(fractf(fabsf(a) * 0.15915494309189535f)); }
+RT_FN float portable_sin(float a) {
     return trig_select(fractf(fabsf(a - 1.5707963267948966f) * 0.15915494309189535f));
 }
 // returns {sin, cos} like Ref::portable_sincos
-RT_DEV v2 portable_sincos(float a) { return v2{portable_sin(a), portable_cos(a)}; }
+RT_FN v2 portable_sincos(float a) { return v2{portable_sin(a), portable_cos(a)}; }
 
 RT_DEV float asin_tail(float x) {
     return (kPi / 2) - ((x + 2.71745038f) * x + 14.0375338f) * (0.00440413551f * ((x - 8.31223679f) * x + 25.3978882f)) *
                            sqrtf(1 - x);
 }
-RT_DEV float portable_asinf(float x) {
+RT_FN float portable_asinf(float x) {
     if (fabsf(x) > 0.57f) {
         const float ret = asin_tail(fabsf(x));
         return (x < 0.0f) ? -ret : ret;
@@ -182,7 +185,7 @@ RT_DEV float portable_asinf(float x) {
                        (x2 * ((x2 - 1.48268414f) * x2 + 2.05554748f));
     }
 }
-RT_DEV float portable_acosf(float x) {
+RT_FN float portable_acosf(float x) {
     if (x < -0.62f) {
         return kPi - (((x - 2.71850395f) * x + 14.7303705f)) * (0.00393401226f * ((x + 8.60734272f) * x + 27.0927486f)) *
                          sqrtf(1 + x);
@@ -201,7 +204,7 @@ RT_DEV float portable_acosf(float x) {
 // arithmetic).  The reference calls libm acosf in slerp() (CoreRef.cpp:1110-1126) and for spot lights; CUDA's acosf
 // is a different <=1-ulp approximation, and one ulp in a sampled direction is enough to flip a later discrete
 // decision.  tests/test_libm.py checks this restatement against the host libm over the whole [-1,1] domain.
-RT_DEV float libm_acosf(float x) {
+RT_FN float libm_acosf(float x) {
     const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f,
                 pio2_lo = 7.5497894159e-08f, pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f,
                 pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f, pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f,
@@ -287,7 +290,7 @@ RT_DEV v3 world_from_tangent(v3 T, v3 B, v3 N, v3 V) { return V.x * T + V.y * B 
 RT_DEV v3 tangent_from_world(v3 T, v3 B, v3 N, v3 V) { return v3{dot(V, T), dot(V, B), dot(V, N)}; }
 
 // CoreRef.cpp:675-688
-RT_DEV void create_tbn(v3 N, v3 &T, v3 &B) {
+RT_FN void create_tbn(v3 N, v3 &T, v3 &B) {
     v3 U;
     if (fabsf(N.y) < 0.999f) {
         U = v3{0.0f, 1.0f, 0.0f};
@@ -330,7 +333,7 @@ RT_DEV uint32_t laine_karras(uint32_t x, uint32_t seed) {
 }
 RT_DEV uint32_t owen_scramble(uint32_t x, uint32_t seed) { return __brev(laine_karras(__brev(x), seed)); }
 RT_DEV float scramble_unorm(uint32_t seed, uint32_t val) { return float(owen_scramble(val, seed) >> 8) / 16777216.0f; }
-RT_DEV v2 rand2d(uint32_t dim, uint32_t seed, int sample, const uint32_t *__restrict__ seq) {
+RT_FN v2 rand2d(uint32_t dim, uint32_t seed, int sample, const uint32_t *__restrict__ seq) {
     const uint32_t sd = owen_scramble(dim, seed) & (kRandDims - 1);
     const uint32_t si = owen_scramble(uint32_t(sample), hash_combine(seed, dim)) & (kRandSamples - 1);
     const uint2 s = __ldg(reinterpret_cast<const uint2 *>(seq + sd * 2 * kRandSamples + 2 * si));

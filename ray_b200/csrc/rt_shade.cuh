@@ -50,7 +50,7 @@ struct Surface {
     v3 P, T, B, N, plane_N;
 };
 
-RT_DEV v2 calc_alpha(float roughness, float anisotropy, float regularize_alpha) {
+RT_FN v2 calc_alpha(float roughness, float anisotropy, float regularize_alpha) {
     const float roughness2 = sqr(roughness);
     const float aspect = sqrtf(1.0f - 0.9f * anisotropy);
     v2 alpha = v2{roughness2 / aspect, roughness2 * aspect};
@@ -73,7 +73,7 @@ struct LobeWeights {
     float diffuse, specular, clearcoat, refraction;
 };
 
-RT_DEV LobeWeights get_lobe_weights(float base_color_lum, float spec_color_lum, float specular, float metallic,
+RT_FN LobeWeights get_lobe_weights(float base_color_lum, float spec_color_lum, float specular, float metallic,
                                     float transmission, float clearcoat) {
     LobeWeights w;
     w.diffuse = base_color_lum * (1.0f - metallic) * (1.0f - transmission);
@@ -91,7 +91,7 @@ RT_DEV LobeWeights get_lobe_weights(float base_color_lum, float spec_color_lum, 
     return w;
 }
 
-RT_DEV float fresnel_dielectric_cos(float cosi, float eta) {
+RT_FN float fresnel_dielectric_cos(float cosi, float eta) {
     const float c = fabsf(cosi);
     float g = eta * eta - 1 + c * c;
     float result;
@@ -131,19 +131,19 @@ RT_DEV v3 sample_vndf_sphcap_bounded(v3 Ve, v3 Vh, v2 alpha, v2 rand) {
     return v3{x, y, z} + Vh;
 }
 
-RT_DEV v3 sample_ggx_vndf(v3 Ve, v2 alpha, v2 rand) {
+RT_FN v3 sample_ggx_vndf(v3 Ve, v2 alpha, v2 rand) {
     const v3 Vh = normalize(v3{alpha.x * Ve.x, alpha.y * Ve.y, Ve.z});
     const v3 Nh = sample_vndf_sphcap(Vh, rand);
     return normalize(v3{alpha.x * Nh.x, alpha.y * Nh.y, fmaxf(0.0f, Nh.z)});
 }
 
-RT_DEV v3 sample_ggx_vndf_bounded(v3 Ve, v2 alpha, v2 rand) {
+RT_FN v3 sample_ggx_vndf_bounded(v3 Ve, v2 alpha, v2 rand) {
     const v3 Vh = normalize(v3{alpha.x * Ve.x, alpha.y * Ve.y, Ve.z});
     const v3 Nh = sample_vndf_sphcap_bounded(Ve, Vh, alpha, rand);
     return normalize(v3{alpha.x * Nh.x, alpha.y * Nh.y, fmaxf(0.0f, Nh.z)});
 }
 
-RT_DEV float ggx_vndf_reflection_bounded_pdf(float D, v3 view_dir_ts, v2 alpha) {
+RT_FN float ggx_vndf_reflection_bounded_pdf(float D, v3 view_dir_ts, v2 alpha) {
     const v2 ai = alpha * v2{view_dir_ts.x, view_dir_ts.y};
     const float len2 = dot(ai, ai);
     const float t = sqrtf(len2 + view_dir_ts.z * view_dir_ts.z);
@@ -157,7 +157,7 @@ RT_DEV float ggx_vndf_reflection_bounded_pdf(float D, v3 view_dir_ts, v2 alpha) 
     return D * (t - view_dir_ts.z) / (2.0f * len2);
 }
 
-RT_DEV float G1(v3 Ve, v2 alpha) {
+RT_FN float G1(v3 Ve, v2 alpha) {
     alpha = alpha * alpha;
     const float delta =
         (-1.0f + sqrtf(1.0f + safe_div_pos(alpha.x * sqr(Ve.x) + alpha.y * sqr(Ve.y), sqr(Ve.z)))) / 2.0f;
@@ -174,7 +174,7 @@ RT_DEV float D_GTR1(float NDotH, float a) {
     return (a2 - 1.0f) / (kPi * logf(a2) * t);
 }
 
-RT_DEV float D_GGX(v3 H, v2 alpha) {
+RT_FN float D_GGX(v3 H, v2 alpha) {
     if (H.z == 0.0f) {
         return 0.0f;
     }
@@ -237,7 +237,7 @@ RT_DEV float brdf_principled_diffuse(v3 V, v3 N, v3 L, v3 H, float roughness) {
     return mixf(1.0f, Fd90, FL) * mixf(1.0f, Fd90, FV);
 }
 
-RT_DEV c4 eval_oren_diffuse(v3 V, v3 N, v3 L, float roughness, v3 base_color) {
+RT_FN c4 eval_oren_diffuse(v3 V, v3 N, v3 L, float roughness, v3 base_color) {
     const float sigma = roughness;
     const float div = 1.0f / (kPi + ((3.0f * kPi - 4.0f) / 6.0f) * sigma);
     const float a = 1.0f * div;
@@ -252,7 +252,7 @@ RT_DEV c4 eval_oren_diffuse(v3 V, v3 N, v3 L, float roughness, v3 base_color) {
     return c4{is * base_color.x, is * base_color.y, is * base_color.z, 0.5f / kPi};
 }
 
-RT_DEV c4 sample_oren_diffuse(v3 T, v3 B, v3 N, v3 I, float roughness, v3 base_color, v2 rand, v3 &out_V) {
+RT_FN c4 sample_oren_diffuse(v3 T, v3 B, v3 N, v3 I, float roughness, v3 base_color, v2 rand, v3 &out_V) {
     const float phi = 2 * kPi * rand.y;
     const v2 sc = portable_sincos(phi);
     const float cos_phi = sc.y, sin_phi = sc.x;
@@ -263,7 +263,7 @@ RT_DEV c4 sample_oren_diffuse(v3 T, v3 B, v3 N, v3 I, float roughness, v3 base_c
     return eval_oren_diffuse(-I, N, out_V, roughness, base_color);
 }
 
-RT_DEV c4 eval_principled_diffuse(v3 V, v3 N, v3 L, float roughness, v3 base_color, v3 sheen_color) {
+RT_FN c4 eval_principled_diffuse(v3 V, v3 N, v3 L, float roughness, v3 base_color, v3 sheen_color) {
     const float weight = 1.0f;
     const float pdf = dot(N, L) / kPi;
     v3 H = normalize(L + V);
@@ -276,7 +276,7 @@ RT_DEV c4 eval_principled_diffuse(v3 V, v3 N, v3 L, float roughness, v3 base_col
     return c4{diff_col.x, diff_col.y, diff_col.z, pdf};
 }
 
-RT_DEV c4 sample_principled_diffuse(v3 T, v3 B, v3 N, v3 I, float roughness, v3 base_color, v3 sheen_color, v2 rand,
+RT_FN c4 sample_principled_diffuse(v3 T, v3 B, v3 N, v3 I, float roughness, v3 base_color, v3 sheen_color, v2 rand,
                                     v3 &out_V) {
     const float phi = 2 * kPi * rand.y;
     const v2 sc = portable_sincos(phi);
@@ -288,7 +288,7 @@ RT_DEV c4 sample_principled_diffuse(v3 T, v3 B, v3 N, v3 I, float roughness, v3 
     return eval_principled_diffuse(-I, N, out_V, roughness, base_color, sheen_color);
 }
 
-RT_DEV c4 eval_ggx_specular(v3 view_dir_ts, v3 sampled_normal_ts, v3 reflected_dir_ts, v2 alpha, float spec_ior,
+RT_FN c4 eval_ggx_specular(v3 view_dir_ts, v3 sampled_normal_ts, v3 reflected_dir_ts, v2 alpha, float spec_ior,
                             float spec_F0, v3 spec_col, v3 spec_col_90) {
     const float D = D_GGX(sampled_normal_ts, alpha);
     const float G = G1(view_dir_ts, alpha) * G1(reflected_dir_ts, alpha);
@@ -302,7 +302,7 @@ RT_DEV c4 eval_ggx_specular(v3 view_dir_ts, v3 sampled_normal_ts, v3 reflected_d
     return c4{F.x, F.y, F.z, pdf};
 }
 
-RT_DEV c4 sample_ggx_specular(v3 T, v3 B, v3 N, v3 I, v2 alpha, float spec_ior, float spec_F0, v3 spec_col,
+RT_FN c4 sample_ggx_specular(v3 T, v3 B, v3 N, v3 I, v2 alpha, float spec_ior, float spec_F0, v3 spec_col,
                               v3 spec_col_90, v2 rand, v3 &out_V) {
     if (alpha.x * alpha.y < 1e-7f) {
         const v3 V = reflect(I, N, dot(N, I));
@@ -320,7 +320,7 @@ RT_DEV c4 sample_ggx_specular(v3 T, v3 B, v3 N, v3 I, v2 alpha, float spec_ior, 
                              spec_col_90);
 }
 
-RT_DEV c4 eval_ggx_refraction(v3 view_dir_ts, v3 sampled_normal_ts, v3 refr_dir_ts, v2 alpha, float eta, v3 refr_col) {
+RT_FN c4 eval_ggx_refraction(v3 view_dir_ts, v3 sampled_normal_ts, v3 refr_dir_ts, v2 alpha, float eta, v3 refr_col) {
     if (refr_dir_ts.z >= 0.0f || view_dir_ts.z <= 0.0f || alpha.x * alpha.y < 1e-7f) {
         return c4{0.0f, 0.0f, 0.0f, 0.0f};
     }
@@ -334,7 +334,7 @@ RT_DEV c4 eval_ggx_refraction(v3 view_dir_ts, v3 sampled_normal_ts, v3 refr_dir_
 }
 
 // out_V.w of the reference (the `m` term) is never read by the callers on this path; only xyz is returned.
-RT_DEV c4 sample_ggx_refraction(v3 T, v3 B, v3 N, v3 I, v2 alpha, float eta, v3 refr_col, v2 rand, v3 &out_V) {
+RT_FN c4 sample_ggx_refraction(v3 T, v3 B, v3 N, v3 I, v2 alpha, float eta, v3 refr_col, v2 rand, v3 &out_V) {
     if (alpha.x * alpha.y < 1e-7f) {
         const float cosi = -dot(I, N);
         const float cost2 = 1.0f - eta * eta * (1.0f - cosi * cosi);
@@ -359,7 +359,7 @@ RT_DEV c4 sample_ggx_refraction(v3 T, v3 B, v3 N, v3 I, v2 alpha, float eta, v3 
     return F;
 }
 
-RT_DEV c4 eval_clearcoat(v3 view_dir_ts, v3 sampled_normal_ts, v3 reflected_dir_ts, float clearcoat_roughness2,
+RT_FN c4 eval_clearcoat(v3 view_dir_ts, v3 sampled_normal_ts, v3 reflected_dir_ts, float clearcoat_roughness2,
                          float clearcoat_ior, float clearcoat_F0) {
     const float D = D_GTR1(sampled_normal_ts.z, clearcoat_roughness2);
     const v2 clearcoat_alpha = v2{0.25f * 0.25f, 0.25f * 0.25f};
@@ -374,7 +374,7 @@ RT_DEV c4 eval_clearcoat(v3 view_dir_ts, v3 sampled_normal_ts, v3 reflected_dir_
     return c4{F, F, F, pdf};
 }
 
-RT_DEV c4 sample_clearcoat(v3 T, v3 B, v3 N, v3 I, float clearcoat_roughness2, float clearcoat_ior, float clearcoat_F0,
+RT_FN c4 sample_clearcoat(v3 T, v3 B, v3 N, v3 I, float clearcoat_roughness2, float clearcoat_ior, float clearcoat_F0,
                            v2 rand, v3 &out_V) {
     if (sqr(clearcoat_roughness2) < 1e-7f) {
         const v3 V = reflect(I, N, dot(N, I));
@@ -427,6 +427,496 @@ struct ShadeOut {
     float aov_depth;
     bool wrote_aov;
 };
+
+// Everything a material-node branch of ShadeSurface reads or writes.  The branches are separate (non-inlined) functions
+// so the kernel's hot instruction footprint is the branch actually taken, not all five (see RT_FN in rt_math.cuh).
+struct MatCtx {
+    const PassSettings *ps;
+    const RayD *ray;
+    const ShadeScene *sc;
+    const Hit *inter;
+    Surface surf;
+    LightSample ls;
+    const Material *mat;
+    const MeshInstance *mi;
+    const Vertex *vtx1, *vtx2, *vtx3;
+    RayD *new_ray;
+    ShadowRayD *sh_r;
+    v3 col;
+    v3 I, ro, base_color, tint_color;
+    float N_dot_L, roughness, mix_weight, mix_rand, regularize_alpha, ext_ior, base_color_lum;
+    v2 rand_bsdf;
+    bool use_mis, is_backfacing;
+    int diff_d, spec_d, refr_d, total_d;
+    uint32_t tri_index;
+    uint32_t *tl_stack;
+    float *tl_factors;
+};
+
+RT_FN void shade_node_diffuse(MatCtx &c) {
+    const PassSettings &ps = *c.ps;
+    const RayD &ray = *c.ray;
+    const ShadeScene &sc = *c.sc;
+    const Hit &inter = *c.inter;
+    const Surface &surf = c.surf;
+    const LightSample &ls = c.ls;
+    const Material *mat = c.mat;
+    const MeshInstance *mi = c.mi;
+    const Vertex &v1 = *c.vtx1, &v2_ = *c.vtx2, &v3_ = *c.vtx3;
+    RayD &new_ray = *c.new_ray;
+    ShadowRayD &sh_r = *c.sh_r;
+    v3 &col = c.col;
+    const v3 I = c.I, ro = c.ro, base_color = c.base_color, tint_color = c.tint_color;
+    const float N_dot_L = c.N_dot_L, roughness = c.roughness, mix_weight = c.mix_weight, mix_rand = c.mix_rand,
+                regularize_alpha = c.regularize_alpha, ext_ior = c.ext_ior, base_color_lum = c.base_color_lum;
+    const v2 rand_bsdf = c.rand_bsdf;
+    const bool use_mis = c.use_mis, is_backfacing = c.is_backfacing;
+    const int diff_d = c.diff_d, spec_d = c.spec_d, refr_d = c.refr_d, total_d = c.total_d;
+    const uint32_t tri_index = c.tri_index;
+    uint32_t *tl_stack = c.tl_stack;
+    float *tl_factors = c.tl_factors;
+    (void)ps; (void)ray; (void)sc; (void)inter; (void)surf; (void)ls; (void)mat; (void)mi; (void)v1; (void)v2_; (void)v3_;
+    (void)new_ray; (void)sh_r; (void)col; (void)I; (void)ro; (void)base_color; (void)tint_color; (void)N_dot_L;
+    (void)roughness; (void)mix_weight; (void)mix_rand; (void)regularize_alpha; (void)ext_ior; (void)base_color_lum;
+    (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
+    (void)tri_index; (void)tl_stack; (void)tl_factors;
+    if (ls.pdf > 0.0f && (ls.ray_flags & (1u << RAY_DIFFUSE)) != 0 && N_dot_L > 0.0f) {
+        // Evaluate_DiffuseNode :645-672
+        const c4 diff_col = eval_oren_diffuse(-I, surf.N, ls.L, roughness, base_color);
+        const float bsdf_pdf = diff_col.w;
+        float mis_weight = 1.0f;
+        if (use_mis && ls.area > 0.0f) {
+            mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
+        }
+        const v3 lcol = ls.col * v3{diff_col.x, diff_col.y, diff_col.z} * (mix_weight * mis_weight / ls.pdf);
+        if (!ls.cast_shadow) {
+            col += lcol;
+        } else {
+            sh_r.o = offset_ray(surf.P, surf.plane_N);
+            sh_r.c = lcol;
+        }
+    }
+    if (diff_d < ps.max_diff_depth && total_d < ps.max_total_depth) {
+        // Sample_DiffuseNode :674-692
+        v3 V;
+        const c4 F = sample_oren_diffuse(surf.T, surf.B, surf.N, I, roughness, base_color, rand_bsdf, V);
+        new_ray.depth = (uint32_t(RAY_DIFFUSE) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(1, 0, 0, 0));
+        new_ray.o = offset_ray(surf.P, surf.plane_N);
+        new_ray.d = V;
+        new_ray.c = v3{F.x * mix_weight / F.w, F.y * mix_weight / F.w, F.z * mix_weight / F.w};
+        new_ray.pdf = F.w;
+        new_ray.cone_spread += kMaxConeSpreadInc;
+    }
+}
+
+RT_FN void shade_node_glossy(MatCtx &c) {
+    const PassSettings &ps = *c.ps;
+    const RayD &ray = *c.ray;
+    const ShadeScene &sc = *c.sc;
+    const Hit &inter = *c.inter;
+    const Surface &surf = c.surf;
+    const LightSample &ls = c.ls;
+    const Material *mat = c.mat;
+    const MeshInstance *mi = c.mi;
+    const Vertex &v1 = *c.vtx1, &v2_ = *c.vtx2, &v3_ = *c.vtx3;
+    RayD &new_ray = *c.new_ray;
+    ShadowRayD &sh_r = *c.sh_r;
+    v3 &col = c.col;
+    const v3 I = c.I, ro = c.ro, base_color = c.base_color, tint_color = c.tint_color;
+    const float N_dot_L = c.N_dot_L, roughness = c.roughness, mix_weight = c.mix_weight, mix_rand = c.mix_rand,
+                regularize_alpha = c.regularize_alpha, ext_ior = c.ext_ior, base_color_lum = c.base_color_lum;
+    const v2 rand_bsdf = c.rand_bsdf;
+    const bool use_mis = c.use_mis, is_backfacing = c.is_backfacing;
+    const int diff_d = c.diff_d, spec_d = c.spec_d, refr_d = c.refr_d, total_d = c.total_d;
+    const uint32_t tri_index = c.tri_index;
+    uint32_t *tl_stack = c.tl_stack;
+    float *tl_factors = c.tl_factors;
+    (void)ps; (void)ray; (void)sc; (void)inter; (void)surf; (void)ls; (void)mat; (void)mi; (void)v1; (void)v2_; (void)v3_;
+    (void)new_ray; (void)sh_r; (void)col; (void)I; (void)ro; (void)base_color; (void)tint_color; (void)N_dot_L;
+    (void)roughness; (void)mix_weight; (void)mix_rand; (void)regularize_alpha; (void)ext_ior; (void)base_color_lum;
+    (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
+    (void)tri_index; (void)tl_stack; (void)tl_factors;
+    const float specular = 0.5f;
+    const float spec_ior = (2.0f / (1.0f - sqrtf(0.08f * specular))) - 1.0f;
+    const float spec_F0 = fresnel_dielectric_cos(1.0f, spec_ior);
+    if (ls.pdf > 0.0f && (ls.ray_flags & (1u << RAY_SPECULAR)) != 0 && N_dot_L > 0.0f) {
+        // Evaluate_GlossyNode :694-730
+        const v3 H = normalize(ls.L - I);
+        const v3 view_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, -I);
+        const v3 light_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, ls.L);
+        const v3 sampled_normal_ts = tangent_from_world(surf.T, surf.B, surf.N, H);
+        const v2 alpha = calc_alpha(roughness, 0.0f, regularize_alpha);
+        if (!(alpha.x * alpha.y < 1e-7f)) {
+            const c4 spec_col = eval_ggx_specular(view_dir_ts, sampled_normal_ts, light_dir_ts, alpha, spec_ior,
+                                                  spec_F0, base_color, base_color);
+            const float bsdf_pdf = spec_col.w;
+            float mis_weight = 1.0f;
+            if (use_mis && ls.area > 0.0f) {
+                mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
+            }
+            const v3 lcol = ls.col * v3{spec_col.x, spec_col.y, spec_col.z} * (mix_weight * mis_weight / ls.pdf);
+            if (!ls.cast_shadow) {
+                col += lcol;
+            } else {
+                sh_r.o = offset_ray(surf.P, surf.plane_N);
+                sh_r.c = lcol;
+            }
+        }
+    }
+    if (spec_d < ps.max_spec_depth && total_d < ps.max_total_depth) {
+        // Sample_GlossyNode :732-752
+        const v2 alpha = calc_alpha(roughness, 0.0f, regularize_alpha);
+        v3 V;
+        const c4 F = sample_ggx_specular(surf.T, surf.B, surf.N, I, alpha, spec_ior, spec_F0, base_color,
+                                         base_color, rand_bsdf, V);
+        new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
+        new_ray.o = offset_ray(surf.P, surf.plane_N);
+        new_ray.d = V;
+        const float k = safe_div_pos(mix_weight, F.w);
+        new_ray.c = v3{F.x * k, F.y * k, F.z * k};
+        new_ray.pdf = F.w;
+        new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
+    }
+}
+
+RT_FN void shade_node_refractive(MatCtx &c) {
+    const PassSettings &ps = *c.ps;
+    const RayD &ray = *c.ray;
+    const ShadeScene &sc = *c.sc;
+    const Hit &inter = *c.inter;
+    const Surface &surf = c.surf;
+    const LightSample &ls = c.ls;
+    const Material *mat = c.mat;
+    const MeshInstance *mi = c.mi;
+    const Vertex &v1 = *c.vtx1, &v2_ = *c.vtx2, &v3_ = *c.vtx3;
+    RayD &new_ray = *c.new_ray;
+    ShadowRayD &sh_r = *c.sh_r;
+    v3 &col = c.col;
+    const v3 I = c.I, ro = c.ro, base_color = c.base_color, tint_color = c.tint_color;
+    const float N_dot_L = c.N_dot_L, roughness = c.roughness, mix_weight = c.mix_weight, mix_rand = c.mix_rand,
+                regularize_alpha = c.regularize_alpha, ext_ior = c.ext_ior, base_color_lum = c.base_color_lum;
+    const v2 rand_bsdf = c.rand_bsdf;
+    const bool use_mis = c.use_mis, is_backfacing = c.is_backfacing;
+    const int diff_d = c.diff_d, spec_d = c.spec_d, refr_d = c.refr_d, total_d = c.total_d;
+    const uint32_t tri_index = c.tri_index;
+    uint32_t *tl_stack = c.tl_stack;
+    float *tl_factors = c.tl_factors;
+    (void)ps; (void)ray; (void)sc; (void)inter; (void)surf; (void)ls; (void)mat; (void)mi; (void)v1; (void)v2_; (void)v3_;
+    (void)new_ray; (void)sh_r; (void)col; (void)I; (void)ro; (void)base_color; (void)tint_color; (void)N_dot_L;
+    (void)roughness; (void)mix_weight; (void)mix_rand; (void)regularize_alpha; (void)ext_ior; (void)base_color_lum;
+    (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
+    (void)tri_index; (void)tl_stack; (void)tl_factors;
+    if (ls.pdf > 0.0f && (ls.ray_flags & (1u << RAY_REFR)) != 0 && N_dot_L < 0.0f) {
+        // Evaluate_RefractiveNode :754-786
+        const float eta = is_backfacing ? (mat->ior / ext_ior) : (ext_ior / mat->ior);
+        const v3 H = normalize(ls.L - I * eta);
+        const v3 view_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, -I);
+        const v3 light_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, ls.L);
+        const v3 sampled_normal_ts = tangent_from_world(surf.T, surf.B, surf.N, H);
+        const c4 refr_col = eval_ggx_refraction(view_dir_ts, sampled_normal_ts, light_dir_ts,
+                                                calc_alpha(roughness, 0.0f, regularize_alpha), eta, base_color);
+        const float bsdf_pdf = refr_col.w;
+        float mis_weight = 1.0f;
+        if (use_mis && ls.area > 0.0f) {
+            mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
+        }
+        const v3 lcol = ls.col * v3{refr_col.x, refr_col.y, refr_col.z} * (mix_weight * mis_weight / ls.pdf);
+        if (!ls.cast_shadow) {
+            col += lcol;
+        } else {
+            sh_r.o = offset_ray(surf.P, -surf.plane_N);
+            sh_r.c = lcol;
+        }
+    }
+    if (refr_d < ps.max_refr_depth && total_d < ps.max_total_depth) {
+        // Sample_RefractiveNode :788-809
+        const v2 alpha = calc_alpha(roughness, 0.0f, regularize_alpha);
+        const float eta = is_backfacing ? (mat->ior / ext_ior) : (ext_ior / mat->ior);
+        v3 V = v3{0.0f, 0.0f, 0.0f};
+        const c4 F = sample_ggx_refraction(surf.T, surf.B, surf.N, I, alpha, eta, base_color, rand_bsdf, V);
+        new_ray.depth = (uint32_t(RAY_REFR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 0, 1, 0));
+        const float k = safe_div_pos(mix_weight, F.w);
+        new_ray.c = v3{F.x * k, F.y * k, F.z * k};
+        new_ray.pdf = F.w;
+        if (!is_backfacing) {
+            push_ior_stack(new_ray.ior, mat->ior);
+        } else {
+            pop_ior_stack(new_ray.ior);
+        }
+        new_ray.o = offset_ray(surf.P, -surf.plane_N);
+        new_ray.d = V;
+        new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
+    }
+}
+
+RT_FN void shade_node_emissive(MatCtx &c) {
+    const PassSettings &ps = *c.ps;
+    const RayD &ray = *c.ray;
+    const ShadeScene &sc = *c.sc;
+    const Hit &inter = *c.inter;
+    const Surface &surf = c.surf;
+    const LightSample &ls = c.ls;
+    const Material *mat = c.mat;
+    const MeshInstance *mi = c.mi;
+    const Vertex &v1 = *c.vtx1, &v2_ = *c.vtx2, &v3_ = *c.vtx3;
+    RayD &new_ray = *c.new_ray;
+    ShadowRayD &sh_r = *c.sh_r;
+    v3 &col = c.col;
+    const v3 I = c.I, ro = c.ro, base_color = c.base_color, tint_color = c.tint_color;
+    const float N_dot_L = c.N_dot_L, roughness = c.roughness, mix_weight = c.mix_weight, mix_rand = c.mix_rand,
+                regularize_alpha = c.regularize_alpha, ext_ior = c.ext_ior, base_color_lum = c.base_color_lum;
+    const v2 rand_bsdf = c.rand_bsdf;
+    const bool use_mis = c.use_mis, is_backfacing = c.is_backfacing;
+    const int diff_d = c.diff_d, spec_d = c.spec_d, refr_d = c.refr_d, total_d = c.total_d;
+    const uint32_t tri_index = c.tri_index;
+    uint32_t *tl_stack = c.tl_stack;
+    float *tl_factors = c.tl_factors;
+    (void)ps; (void)ray; (void)sc; (void)inter; (void)surf; (void)ls; (void)mat; (void)mi; (void)v1; (void)v2_; (void)v3_;
+    (void)new_ray; (void)sh_r; (void)col; (void)I; (void)ro; (void)base_color; (void)tint_color; (void)N_dot_L;
+    (void)roughness; (void)mix_weight; (void)mix_rand; (void)regularize_alpha; (void)ext_ior; (void)base_color_lum;
+    (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
+    (void)tri_index; (void)tl_stack; (void)tl_factors;
+    float mis_weight = 1.0f;
+    if ((ray.depth & 0x00ffffffu) != 0 && (mat->flags & kMatFlagImpSample)) {
+        const float pdf_factor = eval_tri_light_factor(sc.lights, surf.P, ro, tri_index, tl_stack, tl_factors);
+        const v3 p1 = mk3(v1.p), p2 = mk3(v2_.p), p3 = mk3(v3_.p);
+        float light_forward_len;
+        const v3 light_forward =
+            normalize_len(transform_direction(cross(p2 - p1, p3 - p1), mi->xform), light_forward_len);
+        const float tri_area = 0.5f * light_forward_len;
+        const float cos_theta = fabsf(dot(I, light_forward));
+        if (cos_theta > 0.0f) {
+            float light_pdf = 0.0f;
+            {
+                const v3 P = transform_point(ro, mi->inv_xform);
+                light_pdf = sample_spherical_triangle(P, p1, p2, p3, v2{0.0f, 0.0f}, nullptr) / pdf_factor;
+            }
+            if (light_pdf == 0.0f) {
+                light_pdf = (inter.t * inter.t) / (tri_area * cos_theta * pdf_factor);
+            }
+            mis_weight = power_heuristic(ray.pdf, light_pdf);
+        }
+    }
+    col += mix_weight * mis_weight * mat->tangent_rotation_or_strength * base_color;
+}
+
+RT_FN void shade_node_principled(MatCtx &c) {
+    const PassSettings &ps = *c.ps;
+    const RayD &ray = *c.ray;
+    const ShadeScene &sc = *c.sc;
+    const Hit &inter = *c.inter;
+    const Surface &surf = c.surf;
+    const LightSample &ls = c.ls;
+    const Material *mat = c.mat;
+    const MeshInstance *mi = c.mi;
+    const Vertex &v1 = *c.vtx1, &v2_ = *c.vtx2, &v3_ = *c.vtx3;
+    RayD &new_ray = *c.new_ray;
+    ShadowRayD &sh_r = *c.sh_r;
+    v3 &col = c.col;
+    const v3 I = c.I, ro = c.ro, base_color = c.base_color, tint_color = c.tint_color;
+    const float N_dot_L = c.N_dot_L, roughness = c.roughness, mix_weight = c.mix_weight, mix_rand = c.mix_rand,
+                regularize_alpha = c.regularize_alpha, ext_ior = c.ext_ior, base_color_lum = c.base_color_lum;
+    const v2 rand_bsdf = c.rand_bsdf;
+    const bool use_mis = c.use_mis, is_backfacing = c.is_backfacing;
+    const int diff_d = c.diff_d, spec_d = c.spec_d, refr_d = c.refr_d, total_d = c.total_d;
+    const uint32_t tri_index = c.tri_index;
+    uint32_t *tl_stack = c.tl_stack;
+    float *tl_factors = c.tl_factors;
+    (void)ps; (void)ray; (void)sc; (void)inter; (void)surf; (void)ls; (void)mat; (void)mi; (void)v1; (void)v2_; (void)v3_;
+    (void)new_ray; (void)sh_r; (void)col; (void)I; (void)ro; (void)base_color; (void)tint_color; (void)N_dot_L;
+    (void)roughness; (void)mix_weight; (void)mix_rand; (void)regularize_alpha; (void)ext_ior; (void)base_color_lum;
+    (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
+    (void)tri_index; (void)tl_stack; (void)tl_factors;
+    const float metallic = unorm16(mat->metallic_unorm);
+    const float specular = unorm16(mat->specular_unorm);
+    const float specular_tint = unorm16(mat->specular_tint_unorm);
+    const float transmission = unorm16(mat->transmission_unorm);
+    const float clearcoat = unorm16(mat->clearcoat_unorm);
+    const float clearcoat_roughness = unorm16(mat->clearcoat_roughness_unorm);
+    const float sheen = 2.0f * unorm16(mat->sheen_unorm);
+    const float sheen_tint = unorm16(mat->sheen_tint_unorm);
+
+    const v3 one3 = v3{1.0f, 1.0f, 1.0f};
+    const v3 diff_base_color = base_color;
+    const v3 diff_sheen_color = sheen * mix3(one3, tint_color, sheen_tint);
+    const float diff_roughness = roughness;
+
+    SpecParams spec;
+    spec.tmp_col = mix3(one3, tint_color, specular_tint);
+    spec.tmp_col = mix3(specular * 0.08f * spec.tmp_col, base_color, metallic);
+    spec.roughness = roughness;
+    spec.ior = (2.0f / (1.0f - sqrtf(0.08f * specular))) - 1.0f;
+    spec.F0 = fresnel_dielectric_cos(1.0f, spec.ior);
+    spec.anisotropy = unorm16(mat->anisotropic_unorm);
+
+    CoatParams coat;
+    coat.roughness = clearcoat_roughness;
+    coat.ior = (2.0f / (1.0f - sqrtf(0.08f * clearcoat))) - 1.0f;
+    coat.F0 = fresnel_dielectric_cos(1.0f, coat.ior);
+
+    TransParams trans;
+    trans.roughness = 1.0f - (1.0f - roughness) * (1.0f - unorm16(mat->transmission_roughness_unorm));
+    trans.int_ior = mat->ior;
+    trans.eta = is_backfacing ? (mat->ior / ext_ior) : (ext_ior / mat->ior);
+    trans.fresnel = fresnel_dielectric_cos(dot(I, surf.N), 1.0f / trans.eta);
+    trans.backfacing = is_backfacing;
+
+    const float FN = (fresnel_dielectric_cos(dot(I, surf.N), spec.ior) - spec.F0) / (1.0f - spec.F0);
+    const v3 approx_spec_col = mix3(spec.tmp_col, one3, FN);
+    const float spec_color_lum = lum(approx_spec_col);
+
+    const LobeWeights lobe = get_lobe_weights(mixf(base_color_lum, 1.0f, sheen), spec_color_lum, specular, metallic,
+                                              transmission, clearcoat);
+
+    if (ls.pdf > 0.0f) {
+        // Evaluate_PrincipledNode :811-903
+        v3 lcol = v3{0.0f, 0.0f, 0.0f};
+        float bsdf_pdf = 0.0f;
+        if (lobe.diffuse > 0.0f && N_dot_L > 0.0f && (ls.ray_flags & (1u << RAY_DIFFUSE)) != 0) {
+            const c4 dc = eval_principled_diffuse(-I, surf.N, ls.L, diff_roughness, diff_base_color, diff_sheen_color);
+            bsdf_pdf += lobe.diffuse * dc.w;
+            v3 diff_col = v3{dc.x, dc.y, dc.z};
+            diff_col *= (1.0f - metallic) * (1.0f - transmission);
+            lcol += ls.col * N_dot_L * diff_col / (kPi * ls.pdf);
+        }
+        v3 H;
+        if (N_dot_L > 0.0f) {
+            H = normalize(ls.L - I);
+        } else {
+            H = normalize(ls.L - I * trans.eta);
+        }
+        const v3 view_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, -I);
+        const v3 light_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, ls.L);
+        const v3 sampled_normal_ts = tangent_from_world(surf.T, surf.B, surf.N, H);
+
+        const v2 spec_alpha = calc_alpha(spec.roughness, spec.anisotropy, regularize_alpha);
+        if (lobe.specular > 0.0f && spec_alpha.x * spec_alpha.y >= 1e-7f && N_dot_L > 0.0f &&
+            (ls.ray_flags & (1u << RAY_SPECULAR)) != 0) {
+            const c4 sc4 = eval_ggx_specular(view_dir_ts, sampled_normal_ts, light_dir_ts, spec_alpha, spec.ior,
+                                             spec.F0, spec.tmp_col, one3);
+            bsdf_pdf += lobe.specular * sc4.w;
+            lcol += ls.col * v3{sc4.x, sc4.y, sc4.z} / ls.pdf;
+        }
+        const v2 coat_alpha = calc_alpha(coat.roughness, 0.0f, regularize_alpha);
+        if (lobe.clearcoat > 0.0f && coat_alpha.x * coat_alpha.y >= 1e-7f && N_dot_L > 0.0f &&
+            (ls.ray_flags & (1u << RAY_SPECULAR)) != 0) {
+            const c4 cc = eval_clearcoat(view_dir_ts, sampled_normal_ts, light_dir_ts, coat_alpha.x, coat.ior, coat.F0);
+            bsdf_pdf += lobe.clearcoat * cc.w;
+            lcol += 0.25f * ls.col * v3{cc.x, cc.y, cc.z} / ls.pdf;
+        }
+        if (lobe.refraction > 0.0f) {
+            const v2 refr_spec_alpha = calc_alpha(spec.roughness, 0.0f, regularize_alpha);
+            if (trans.fresnel != 0.0f && refr_spec_alpha.x * refr_spec_alpha.y >= 1e-7f && N_dot_L > 0.0f &&
+                (ls.ray_flags & (1u << RAY_SPECULAR)) != 0) {
+                const c4 sc4 = eval_ggx_specular(view_dir_ts, sampled_normal_ts, light_dir_ts, refr_spec_alpha,
+                                                 1.0f, 0.0f, one3, one3);
+                bsdf_pdf += lobe.refraction * trans.fresnel * sc4.w;
+                lcol += ls.col * v3{sc4.x, sc4.y, sc4.z} * (trans.fresnel / ls.pdf);
+            }
+            const v2 refr_trans_alpha = calc_alpha(trans.roughness, 0.0f, regularize_alpha);
+            if (trans.fresnel != 1.0f && refr_trans_alpha.x * refr_trans_alpha.y >= 1e-7f && N_dot_L < 0.0f &&
+                (ls.ray_flags & (1u << RAY_REFR)) != 0) {
+                const c4 rc = eval_ggx_refraction(view_dir_ts, sampled_normal_ts, light_dir_ts, refr_trans_alpha,
+                                                  trans.eta, diff_base_color);
+                bsdf_pdf += lobe.refraction * (1.0f - trans.fresnel) * rc.w;
+                lcol += ls.col * v3{rc.x, rc.y, rc.z} * ((1.0f - trans.fresnel) / ls.pdf);
+            }
+        }
+        float mis_weight = 1.0f;
+        if (use_mis && ls.area > 0.0f) {
+            mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
+        }
+        lcol *= mix_weight * mis_weight;
+        if (!ls.cast_shadow) {
+            col += lcol;
+        } else {
+            sh_r.o = offset_ray(surf.P, N_dot_L < 0.0f ? -surf.plane_N : surf.plane_N);
+            sh_r.c = lcol;
+        }
+    }
+
+    { // Sample_PrincipledNode :905-1028
+        const int ptotal = diff_d + spec_d + refr_d;
+        if (mix_rand < lobe.diffuse) {
+            if (diff_d < ps.max_diff_depth && ptotal < ps.max_total_depth) {
+                v3 V;
+                const c4 F4 = sample_principled_diffuse(surf.T, surf.B, surf.N, I, diff_roughness, diff_base_color,
+                                                        diff_sheen_color, rand_bsdf, V);
+                const float pdf = F4.w;
+                v3 F = v3{F4.x, F4.y, F4.z};
+                F *= (1.0f - metallic) * (1.0f - transmission);
+                new_ray.depth = (uint32_t(RAY_DIFFUSE) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(1, 0, 0, 0));
+                new_ray.o = offset_ray(surf.P, surf.plane_N);
+                new_ray.d = V;
+                const float k = safe_div_pos(mix_weight, lobe.diffuse);
+                new_ray.c = v3{F.x * k, F.y * k, F.z * k};
+                new_ray.pdf = pdf;
+                new_ray.cone_spread += kMaxConeSpreadInc;
+            }
+        } else if (mix_rand < lobe.diffuse + lobe.specular) {
+            if (spec_d < ps.max_spec_depth && ptotal < ps.max_total_depth) {
+                const v2 alpha = calc_alpha(spec.roughness, spec.anisotropy, regularize_alpha);
+                v3 V;
+                const c4 F = sample_ggx_specular(surf.T, surf.B, surf.N, I, alpha, spec.ior, spec.F0, spec.tmp_col,
+                                                 one3, rand_bsdf, V);
+                const float pdf = F.w * lobe.specular;
+                new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
+                const float k = safe_div_pos(mix_weight, pdf);
+                new_ray.c = v3{F.x * k, F.y * k, F.z * k};
+                new_ray.pdf = pdf;
+                new_ray.o = offset_ray(surf.P, surf.plane_N);
+                new_ray.d = V;
+                new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
+            }
+        } else if (mix_rand < lobe.diffuse + lobe.specular + lobe.clearcoat) {
+            if (spec_d < ps.max_spec_depth && ptotal < ps.max_total_depth) {
+                const float alpha = calc_alpha(coat.roughness, 0.0f, regularize_alpha).x;
+                v3 V;
+                const c4 F = sample_clearcoat(surf.T, surf.B, surf.N, I, alpha, coat.ior, coat.F0, rand_bsdf, V);
+                const float pdf = F.w * lobe.clearcoat;
+                new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
+                const float k = safe_div_pos(mix_weight, pdf);
+                new_ray.c = v3{0.25f * F.x * k, 0.25f * F.y * k, 0.25f * F.z * k};
+                new_ray.pdf = pdf;
+                new_ray.o = offset_ray(surf.P, surf.plane_N);
+                new_ray.d = V;
+                new_ray.cone_spread += kMaxConeSpreadInc * alpha;
+            }
+        } else {
+            float mr = mix_rand;
+            mr -= lobe.diffuse + lobe.specular + lobe.clearcoat;
+            mr = safe_div_pos(mr, lobe.refraction);
+            if (((mr >= trans.fresnel && refr_d < ps.max_refr_depth) || (mr < trans.fresnel && spec_d < ps.max_spec_depth)) &&
+                ptotal < ps.max_total_depth) {
+                c4 F;
+                v3 V = v3{0.0f, 0.0f, 0.0f};
+                if (mr < trans.fresnel) {
+                    const v2 alpha = calc_alpha(spec.roughness, 0.0f, regularize_alpha);
+                    F = sample_ggx_specular(surf.T, surf.B, surf.N, I, alpha, 1.0f, 0.0f, one3, one3, rand_bsdf, V);
+                    new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
+                    new_ray.o = offset_ray(surf.P, surf.plane_N);
+                    new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
+                } else {
+                    const v2 alpha = calc_alpha(trans.roughness, 0.0f, regularize_alpha);
+                    F = sample_ggx_refraction(surf.T, surf.B, surf.N, I, alpha, trans.eta, diff_base_color, rand_bsdf, V);
+                    new_ray.depth = (uint32_t(RAY_REFR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 0, 1, 0));
+                    new_ray.o = offset_ray(surf.P, -surf.plane_N);
+                    new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
+                    if (!trans.backfacing) {
+                        push_ior_stack(new_ray.ior, trans.int_ior);
+                    } else {
+                        pop_ior_stack(new_ray.ior);
+                    }
+                }
+                const float pdf = F.w * lobe.refraction;
+                const float k = safe_div_pos(mix_weight, pdf);
+                new_ray.c = v3{F.x * k, F.y * k, F.z * k};
+                new_ray.pdf = pdf;
+                new_ray.d = V;
+            }
+        }
+    }
+}
 
 // One invocation of Ref::ShadeSurface.  `limits` = {direct, indirect} clamp limits (FLT_MAX when clamping is off).
 RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, const Hit &inter, const RayD &ray,
@@ -711,331 +1201,52 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
     const float regularize_alpha = (diff_depth(ray.depth) > 0) ? ps.regularize_alpha : 0.0f;
     const bool use_mis = (total_d < ps.max_total_depth);
 
-    if (mat->type == NODE_DIFFUSE) {
-        if (ls.pdf > 0.0f && (ls.ray_flags & (1u << RAY_DIFFUSE)) != 0 && N_dot_L > 0.0f) {
-            // Evaluate_DiffuseNode :645-672
-            const c4 diff_col = eval_oren_diffuse(-I, surf.N, ls.L, roughness, base_color);
-            const float bsdf_pdf = diff_col.w;
-            float mis_weight = 1.0f;
-            if (use_mis && ls.area > 0.0f) {
-                mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
-            }
-            const v3 lcol = ls.col * v3{diff_col.x, diff_col.y, diff_col.z} * (mix_weight * mis_weight / ls.pdf);
-            if (!ls.cast_shadow) {
-                col += lcol;
-            } else {
-                sh_r.o = offset_ray(surf.P, surf.plane_N);
-                sh_r.c = lcol;
-            }
+    {
+        MatCtx c;
+        c.ps = &ps;
+        c.ray = &ray;
+        c.sc = &sc;
+        c.inter = &inter;
+        c.surf = surf;
+        c.ls = ls;
+        c.mat = mat;
+        c.mi = mi;
+        c.vtx1 = &v1;
+        c.vtx2 = &v2_;
+        c.vtx3 = &v3_;
+        c.new_ray = &new_ray;
+        c.sh_r = &sh_r;
+        c.col = col;
+        c.I = I;
+        c.ro = ro;
+        c.base_color = base_color;
+        c.tint_color = tint_color;
+        c.N_dot_L = N_dot_L;
+        c.roughness = roughness;
+        c.mix_weight = mix_weight;
+        c.mix_rand = mix_rand;
+        c.regularize_alpha = regularize_alpha;
+        c.ext_ior = ext_ior;
+        c.base_color_lum = base_color_lum;
+        c.rand_bsdf = rand_bsdf;
+        c.use_mis = use_mis;
+        c.is_backfacing = is_backfacing;
+        c.diff_d = diff_d;
+        c.spec_d = spec_d;
+        c.refr_d = refr_d;
+        c.total_d = total_d;
+        c.tri_index = tri_index;
+        c.tl_stack = tl_stack;
+        c.tl_factors = tl_factors;
+        switch (mat->type) {
+        case NODE_DIFFUSE: shade_node_diffuse(c); break;
+        case NODE_GLOSSY: shade_node_glossy(c); break;
+        case NODE_REFRACTIVE: shade_node_refractive(c); break;
+        case NODE_EMISSIVE: shade_node_emissive(c); break;
+        case NODE_PRINCIPLED: shade_node_principled(c); break;
+        default: break;
         }
-        if (diff_d < ps.max_diff_depth && total_d < ps.max_total_depth) {
-            // Sample_DiffuseNode :674-692
-            v3 V;
-            const c4 F = sample_oren_diffuse(surf.T, surf.B, surf.N, I, roughness, base_color, rand_bsdf, V);
-            new_ray.depth = (uint32_t(RAY_DIFFUSE) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(1, 0, 0, 0));
-            new_ray.o = offset_ray(surf.P, surf.plane_N);
-            new_ray.d = V;
-            new_ray.c = v3{F.x * mix_weight / F.w, F.y * mix_weight / F.w, F.z * mix_weight / F.w};
-            new_ray.pdf = F.w;
-            new_ray.cone_spread += kMaxConeSpreadInc;
-        }
-    } else if (mat->type == NODE_GLOSSY) {
-        const float specular = 0.5f;
-        const float spec_ior = (2.0f / (1.0f - sqrtf(0.08f * specular))) - 1.0f;
-        const float spec_F0 = fresnel_dielectric_cos(1.0f, spec_ior);
-        if (ls.pdf > 0.0f && (ls.ray_flags & (1u << RAY_SPECULAR)) != 0 && N_dot_L > 0.0f) {
-            // Evaluate_GlossyNode :694-730
-            const v3 H = normalize(ls.L - I);
-            const v3 view_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, -I);
-            const v3 light_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, ls.L);
-            const v3 sampled_normal_ts = tangent_from_world(surf.T, surf.B, surf.N, H);
-            const v2 alpha = calc_alpha(roughness, 0.0f, regularize_alpha);
-            if (!(alpha.x * alpha.y < 1e-7f)) {
-                const c4 spec_col = eval_ggx_specular(view_dir_ts, sampled_normal_ts, light_dir_ts, alpha, spec_ior,
-                                                      spec_F0, base_color, base_color);
-                const float bsdf_pdf = spec_col.w;
-                float mis_weight = 1.0f;
-                if (use_mis && ls.area > 0.0f) {
-                    mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
-                }
-                const v3 lcol = ls.col * v3{spec_col.x, spec_col.y, spec_col.z} * (mix_weight * mis_weight / ls.pdf);
-                if (!ls.cast_shadow) {
-                    col += lcol;
-                } else {
-                    sh_r.o = offset_ray(surf.P, surf.plane_N);
-                    sh_r.c = lcol;
-                }
-            }
-        }
-        if (spec_d < ps.max_spec_depth && total_d < ps.max_total_depth) {
-            // Sample_GlossyNode :732-752
-            const v2 alpha = calc_alpha(roughness, 0.0f, regularize_alpha);
-            v3 V;
-            const c4 F = sample_ggx_specular(surf.T, surf.B, surf.N, I, alpha, spec_ior, spec_F0, base_color,
-                                             base_color, rand_bsdf, V);
-            new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
-            new_ray.o = offset_ray(surf.P, surf.plane_N);
-            new_ray.d = V;
-            const float k = safe_div_pos(mix_weight, F.w);
-            new_ray.c = v3{F.x * k, F.y * k, F.z * k};
-            new_ray.pdf = F.w;
-            new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
-        }
-    } else if (mat->type == NODE_REFRACTIVE) {
-        if (ls.pdf > 0.0f && (ls.ray_flags & (1u << RAY_REFR)) != 0 && N_dot_L < 0.0f) {
-            // Evaluate_RefractiveNode :754-786
-            const float eta = is_backfacing ? (mat->ior / ext_ior) : (ext_ior / mat->ior);
-            const v3 H = normalize(ls.L - I * eta);
-            const v3 view_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, -I);
-            const v3 light_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, ls.L);
-            const v3 sampled_normal_ts = tangent_from_world(surf.T, surf.B, surf.N, H);
-            const c4 refr_col = eval_ggx_refraction(view_dir_ts, sampled_normal_ts, light_dir_ts,
-                                                    calc_alpha(roughness, 0.0f, regularize_alpha), eta, base_color);
-            const float bsdf_pdf = refr_col.w;
-            float mis_weight = 1.0f;
-            if (use_mis && ls.area > 0.0f) {
-                mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
-            }
-            const v3 lcol = ls.col * v3{refr_col.x, refr_col.y, refr_col.z} * (mix_weight * mis_weight / ls.pdf);
-            if (!ls.cast_shadow) {
-                col += lcol;
-            } else {
-                sh_r.o = offset_ray(surf.P, -surf.plane_N);
-                sh_r.c = lcol;
-            }
-        }
-        if (refr_d < ps.max_refr_depth && total_d < ps.max_total_depth) {
-            // Sample_RefractiveNode :788-809
-            const v2 alpha = calc_alpha(roughness, 0.0f, regularize_alpha);
-            const float eta = is_backfacing ? (mat->ior / ext_ior) : (ext_ior / mat->ior);
-            v3 V = v3{0.0f, 0.0f, 0.0f};
-            const c4 F = sample_ggx_refraction(surf.T, surf.B, surf.N, I, alpha, eta, base_color, rand_bsdf, V);
-            new_ray.depth = (uint32_t(RAY_REFR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 0, 1, 0));
-            const float k = safe_div_pos(mix_weight, F.w);
-            new_ray.c = v3{F.x * k, F.y * k, F.z * k};
-            new_ray.pdf = F.w;
-            if (!is_backfacing) {
-                push_ior_stack(new_ray.ior, mat->ior);
-            } else {
-                pop_ior_stack(new_ray.ior);
-            }
-            new_ray.o = offset_ray(surf.P, -surf.plane_N);
-            new_ray.d = V;
-            new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
-        }
-    } else if (mat->type == NODE_EMISSIVE) {
-        float mis_weight = 1.0f;
-        if ((ray.depth & 0x00ffffffu) != 0 && (mat->flags & kMatFlagImpSample)) {
-            const float pdf_factor = eval_tri_light_factor(sc.lights, surf.P, ro, tri_index, tl_stack, tl_factors);
-            const v3 p1 = mk3(v1.p), p2 = mk3(v2_.p), p3 = mk3(v3_.p);
-            float light_forward_len;
-            const v3 light_forward =
-                normalize_len(transform_direction(cross(p2 - p1, p3 - p1), mi->xform), light_forward_len);
-            const float tri_area = 0.5f * light_forward_len;
-            const float cos_theta = fabsf(dot(I, light_forward));
-            if (cos_theta > 0.0f) {
-                float light_pdf = 0.0f;
-                {
-                    const v3 P = transform_point(ro, mi->inv_xform);
-                    light_pdf = sample_spherical_triangle(P, p1, p2, p3, v2{0.0f, 0.0f}, nullptr) / pdf_factor;
-                }
-                if (light_pdf == 0.0f) {
-                    light_pdf = (inter.t * inter.t) / (tri_area * cos_theta * pdf_factor);
-                }
-                mis_weight = power_heuristic(ray.pdf, light_pdf);
-            }
-        }
-        col += mix_weight * mis_weight * mat->tangent_rotation_or_strength * base_color;
-    } else if (mat->type == NODE_PRINCIPLED) {
-        const float metallic = unorm16(mat->metallic_unorm);
-        const float specular = unorm16(mat->specular_unorm);
-        const float specular_tint = unorm16(mat->specular_tint_unorm);
-        const float transmission = unorm16(mat->transmission_unorm);
-        const float clearcoat = unorm16(mat->clearcoat_unorm);
-        const float clearcoat_roughness = unorm16(mat->clearcoat_roughness_unorm);
-        const float sheen = 2.0f * unorm16(mat->sheen_unorm);
-        const float sheen_tint = unorm16(mat->sheen_tint_unorm);
-
-        const v3 one3 = v3{1.0f, 1.0f, 1.0f};
-        const v3 diff_base_color = base_color;
-        const v3 diff_sheen_color = sheen * mix3(one3, tint_color, sheen_tint);
-        const float diff_roughness = roughness;
-
-        SpecParams spec;
-        spec.tmp_col = mix3(one3, tint_color, specular_tint);
-        spec.tmp_col = mix3(specular * 0.08f * spec.tmp_col, base_color, metallic);
-        spec.roughness = roughness;
-        spec.ior = (2.0f / (1.0f - sqrtf(0.08f * specular))) - 1.0f;
-        spec.F0 = fresnel_dielectric_cos(1.0f, spec.ior);
-        spec.anisotropy = unorm16(mat->anisotropic_unorm);
-
-        CoatParams coat;
-        coat.roughness = clearcoat_roughness;
-        coat.ior = (2.0f / (1.0f - sqrtf(0.08f * clearcoat))) - 1.0f;
-        coat.F0 = fresnel_dielectric_cos(1.0f, coat.ior);
-
-        TransParams trans;
-        trans.roughness = 1.0f - (1.0f - roughness) * (1.0f - unorm16(mat->transmission_roughness_unorm));
-        trans.int_ior = mat->ior;
-        trans.eta = is_backfacing ? (mat->ior / ext_ior) : (ext_ior / mat->ior);
-        trans.fresnel = fresnel_dielectric_cos(dot(I, surf.N), 1.0f / trans.eta);
-        trans.backfacing = is_backfacing;
-
-        const float FN = (fresnel_dielectric_cos(dot(I, surf.N), spec.ior) - spec.F0) / (1.0f - spec.F0);
-        const v3 approx_spec_col = mix3(spec.tmp_col, one3, FN);
-        const float spec_color_lum = lum(approx_spec_col);
-
-        const LobeWeights lobe = get_lobe_weights(mixf(base_color_lum, 1.0f, sheen), spec_color_lum, specular, metallic,
-                                                  transmission, clearcoat);
-
-        if (ls.pdf > 0.0f) {
-            // Evaluate_PrincipledNode :811-903
-            v3 lcol = v3{0.0f, 0.0f, 0.0f};
-            float bsdf_pdf = 0.0f;
-            if (lobe.diffuse > 0.0f && N_dot_L > 0.0f && (ls.ray_flags & (1u << RAY_DIFFUSE)) != 0) {
-                const c4 dc = eval_principled_diffuse(-I, surf.N, ls.L, diff_roughness, diff_base_color, diff_sheen_color);
-                bsdf_pdf += lobe.diffuse * dc.w;
-                v3 diff_col = v3{dc.x, dc.y, dc.z};
-                diff_col *= (1.0f - metallic) * (1.0f - transmission);
-                lcol += ls.col * N_dot_L * diff_col / (kPi * ls.pdf);
-            }
-            v3 H;
-            if (N_dot_L > 0.0f) {
-                H = normalize(ls.L - I);
-            } else {
-                H = normalize(ls.L - I * trans.eta);
-            }
-            const v3 view_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, -I);
-            const v3 light_dir_ts = tangent_from_world(surf.T, surf.B, surf.N, ls.L);
-            const v3 sampled_normal_ts = tangent_from_world(surf.T, surf.B, surf.N, H);
-
-            const v2 spec_alpha = calc_alpha(spec.roughness, spec.anisotropy, regularize_alpha);
-            if (lobe.specular > 0.0f && spec_alpha.x * spec_alpha.y >= 1e-7f && N_dot_L > 0.0f &&
-                (ls.ray_flags & (1u << RAY_SPECULAR)) != 0) {
-                const c4 sc4 = eval_ggx_specular(view_dir_ts, sampled_normal_ts, light_dir_ts, spec_alpha, spec.ior,
-                                                 spec.F0, spec.tmp_col, one3);
-                bsdf_pdf += lobe.specular * sc4.w;
-                lcol += ls.col * v3{sc4.x, sc4.y, sc4.z} / ls.pdf;
-            }
-            const v2 coat_alpha = calc_alpha(coat.roughness, 0.0f, regularize_alpha);
-            if (lobe.clearcoat > 0.0f && coat_alpha.x * coat_alpha.y >= 1e-7f && N_dot_L > 0.0f &&
-                (ls.ray_flags & (1u << RAY_SPECULAR)) != 0) {
-                const c4 cc = eval_clearcoat(view_dir_ts, sampled_normal_ts, light_dir_ts, coat_alpha.x, coat.ior, coat.F0);
-                bsdf_pdf += lobe.clearcoat * cc.w;
-                lcol += 0.25f * ls.col * v3{cc.x, cc.y, cc.z} / ls.pdf;
-            }
-            if (lobe.refraction > 0.0f) {
-                const v2 refr_spec_alpha = calc_alpha(spec.roughness, 0.0f, regularize_alpha);
-                if (trans.fresnel != 0.0f && refr_spec_alpha.x * refr_spec_alpha.y >= 1e-7f && N_dot_L > 0.0f &&
-                    (ls.ray_flags & (1u << RAY_SPECULAR)) != 0) {
-                    const c4 sc4 = eval_ggx_specular(view_dir_ts, sampled_normal_ts, light_dir_ts, refr_spec_alpha,
-                                                     1.0f, 0.0f, one3, one3);
-                    bsdf_pdf += lobe.refraction * trans.fresnel * sc4.w;
-                    lcol += ls.col * v3{sc4.x, sc4.y, sc4.z} * (trans.fresnel / ls.pdf);
-                }
-                const v2 refr_trans_alpha = calc_alpha(trans.roughness, 0.0f, regularize_alpha);
-                if (trans.fresnel != 1.0f && refr_trans_alpha.x * refr_trans_alpha.y >= 1e-7f && N_dot_L < 0.0f &&
-                    (ls.ray_flags & (1u << RAY_REFR)) != 0) {
-                    const c4 rc = eval_ggx_refraction(view_dir_ts, sampled_normal_ts, light_dir_ts, refr_trans_alpha,
-                                                      trans.eta, diff_base_color);
-                    bsdf_pdf += lobe.refraction * (1.0f - trans.fresnel) * rc.w;
-                    lcol += ls.col * v3{rc.x, rc.y, rc.z} * ((1.0f - trans.fresnel) / ls.pdf);
-                }
-            }
-            float mis_weight = 1.0f;
-            if (use_mis && ls.area > 0.0f) {
-                mis_weight = power_heuristic(ls.pdf, bsdf_pdf);
-            }
-            lcol *= mix_weight * mis_weight;
-            if (!ls.cast_shadow) {
-                col += lcol;
-            } else {
-                sh_r.o = offset_ray(surf.P, N_dot_L < 0.0f ? -surf.plane_N : surf.plane_N);
-                sh_r.c = lcol;
-            }
-        }
-
-        { // Sample_PrincipledNode :905-1028
-            const int ptotal = diff_d + spec_d + refr_d;
-            if (mix_rand < lobe.diffuse) {
-                if (diff_d < ps.max_diff_depth && ptotal < ps.max_total_depth) {
-                    v3 V;
-                    const c4 F4 = sample_principled_diffuse(surf.T, surf.B, surf.N, I, diff_roughness, diff_base_color,
-                                                            diff_sheen_color, rand_bsdf, V);
-                    const float pdf = F4.w;
-                    v3 F = v3{F4.x, F4.y, F4.z};
-                    F *= (1.0f - metallic) * (1.0f - transmission);
-                    new_ray.depth = (uint32_t(RAY_DIFFUSE) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(1, 0, 0, 0));
-                    new_ray.o = offset_ray(surf.P, surf.plane_N);
-                    new_ray.d = V;
-                    const float k = safe_div_pos(mix_weight, lobe.diffuse);
-                    new_ray.c = v3{F.x * k, F.y * k, F.z * k};
-                    new_ray.pdf = pdf;
-                    new_ray.cone_spread += kMaxConeSpreadInc;
-                }
-            } else if (mix_rand < lobe.diffuse + lobe.specular) {
-                if (spec_d < ps.max_spec_depth && ptotal < ps.max_total_depth) {
-                    const v2 alpha = calc_alpha(spec.roughness, spec.anisotropy, regularize_alpha);
-                    v3 V;
-                    const c4 F = sample_ggx_specular(surf.T, surf.B, surf.N, I, alpha, spec.ior, spec.F0, spec.tmp_col,
-                                                     one3, rand_bsdf, V);
-                    const float pdf = F.w * lobe.specular;
-                    new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
-                    const float k = safe_div_pos(mix_weight, pdf);
-                    new_ray.c = v3{F.x * k, F.y * k, F.z * k};
-                    new_ray.pdf = pdf;
-                    new_ray.o = offset_ray(surf.P, surf.plane_N);
-                    new_ray.d = V;
-                    new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
-                }
-            } else if (mix_rand < lobe.diffuse + lobe.specular + lobe.clearcoat) {
-                if (spec_d < ps.max_spec_depth && ptotal < ps.max_total_depth) {
-                    const float alpha = calc_alpha(coat.roughness, 0.0f, regularize_alpha).x;
-                    v3 V;
-                    const c4 F = sample_clearcoat(surf.T, surf.B, surf.N, I, alpha, coat.ior, coat.F0, rand_bsdf, V);
-                    const float pdf = F.w * lobe.clearcoat;
-                    new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
-                    const float k = safe_div_pos(mix_weight, pdf);
-                    new_ray.c = v3{0.25f * F.x * k, 0.25f * F.y * k, 0.25f * F.z * k};
-                    new_ray.pdf = pdf;
-                    new_ray.o = offset_ray(surf.P, surf.plane_N);
-                    new_ray.d = V;
-                    new_ray.cone_spread += kMaxConeSpreadInc * alpha;
-                }
-            } else {
-                float mr = mix_rand;
-                mr -= lobe.diffuse + lobe.specular + lobe.clearcoat;
-                mr = safe_div_pos(mr, lobe.refraction);
-                if (((mr >= trans.fresnel && refr_d < ps.max_refr_depth) || (mr < trans.fresnel && spec_d < ps.max_spec_depth)) &&
-                    ptotal < ps.max_total_depth) {
-                    c4 F;
-                    v3 V = v3{0.0f, 0.0f, 0.0f};
-                    if (mr < trans.fresnel) {
-                        const v2 alpha = calc_alpha(spec.roughness, 0.0f, regularize_alpha);
-                        F = sample_ggx_specular(surf.T, surf.B, surf.N, I, alpha, 1.0f, 0.0f, one3, one3, rand_bsdf, V);
-                        new_ray.depth = (uint32_t(RAY_SPECULAR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 1, 0, 0));
-                        new_ray.o = offset_ray(surf.P, surf.plane_N);
-                        new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
-                    } else {
-                        const v2 alpha = calc_alpha(trans.roughness, 0.0f, regularize_alpha);
-                        F = sample_ggx_refraction(surf.T, surf.B, surf.N, I, alpha, trans.eta, diff_base_color, rand_bsdf, V);
-                        new_ray.depth = (uint32_t(RAY_REFR) << 28) | ((ray.depth & 0x0fffffffu) + pack_depth(0, 0, 1, 0));
-                        new_ray.o = offset_ray(surf.P, -surf.plane_N);
-                        new_ray.cone_spread += kMaxConeSpreadInc * fminf(alpha.x, alpha.y);
-                        if (!trans.backfacing) {
-                            push_ior_stack(new_ray.ior, trans.int_ior);
-                        } else {
-                            pop_ior_stack(new_ray.ior);
-                        }
-                    }
-                    const float pdf = F.w * lobe.refraction;
-                    const float k = safe_div_pos(mix_weight, pdf);
-                    new_ray.c = v3{F.x * k, F.y * k, F.z * k};
-                    new_ray.pdf = pdf;
-                    new_ray.d = V;
-                }
-            }
-        }
+        col = c.col;
     }
 
     const bool can_terminate_path = total_d > ps.min_total_depth;
