@@ -25,6 +25,7 @@
 #ifndef RAY_CUDA_H
 #define RAY_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -139,6 +140,17 @@ int rc_reset_stats(rc_ctx *ctx);
 /* device-side time (ms, CUDA events on the context stream) of each kernel family accumulated since rc_reset_stats:
  * [0] raygen [1] trace_closest [2] shade [3] trace_shadow [4] sort [5] resolve */
 int rc_get_kernel_ms(rc_ctx *ctx, double ms[6], uint64_t launches[6]);
+
+/* ---- helpers for callers that time or stage data themselves ---- */
+/* pinned (page-locked) host memory for readback mirrors / staging; NULL on failure */
+void *rc_host_alloc(size_t bytes);
+void rc_host_free(void *p);
+/* device address of a frame buffer plane (RC_BUF_*), for zero-copy consumers in the same process (e.g. an NCCL gather
+ * of the accumulated image); the plane is w*h RGBA float, row pitch = w pixels */
+void *rc_device_ptr(rc_ctx *ctx, int which);
+/* user timing events on the context's stream: slot 0..7 */
+int rc_event_record(rc_ctx *ctx, int slot);
+int rc_event_elapsed_ms(rc_ctx *ctx, int slot_a, int slot_b, float *ms);
 
 /* ---- stage entry points (host AoS buffers in the reference's layouts; see header comment) ---- */
 /* rays_out: ray_data_t[rect.w*rect.h] (72 B), hits_out: hit_data_t[...] (20 B); *count_out = rays generated. */

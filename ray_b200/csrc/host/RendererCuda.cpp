@@ -1,0 +1,290 @@
+// RendererCuda.cpp -- see RendererCuda.h.
+#include "RendererCuda.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace RayB200 {
+
+LogNull g_null_log;
+LogStdout g_stdout_log;
+
+static void vlog(const char *fmt, va_list vl) {
+    vprintf(fmt, vl);
+    putc('\n', stdout);
+}
+void LogStdout::Info(const char *fmt, ...) {
+    va_list vl;
+    va_start(vl, fmt);
+    vlog(fmt, vl);
+    va_end(vl);
+}
+void LogStdout::Warning(const char *fmt, ...) {
+    va_list vl;
+    va_start(vl, fmt);
+    vlog(fmt, vl);
+    va_end(vl);
+}
+void LogStdout::Error(const char *fmt, ...) {
+    va_list vl;
+    va_start(vl, fmt);
+    vlog(fmt, vl);
+    va_end(vl);
+}
+
+// reference RendererBase.cpp:6-48
+std::string_view RendererTypeName(const eRendererType rt) {
+    switch (rt) {
+    case eRendererType::Reference: return "REF";
+    case eRendererType::SIMD_SSE41: return "SSE41";
+    case eRendererType::SIMD_AVX: return "AVX";
+    case eRendererType::SIMD_AVX2: return "AVX2";
+    case eRendererType::SIMD_AVX512: return "AVX512";
+    case eRendererType::SIMD_NEON: return "NEON";
+    case eRendererType::Vulkan: return "VK";
+    case eRendererType::DirectX12: return "DX";
+    case eRendererType::CUDA: return "CUDA";
+    }
+    return "";
+}
+eRendererType RendererTypeFromName(std::string_view name) {
+    for (uint32_t i = 0; i <= uint32_t(eRendererType::CUDA); ++i) {
+        if (RendererTypeName(eRendererType(i)) == name) {
+            return eRendererType(i);
+        }
+    }
+    return eRendererType::Reference;
+}
+
+const char *Version() { return "ray-b200 0.1 (hot path of sergcpp/Ray v0.4.0)"; }
+
+// reference Ray.cpp:53-133: try the backend, log and fall through when its constructor throws
+RendererBase *CreateRenderer(const settings_t &s, ILog *log, const ParallelFor &, const uint32_t enabled_types) {
+    if (enabled_types & (1u << uint32_t(eRendererType::CUDA))) {
+        log->Info("Ray: Creating CUDA renderer %ix%i", s.w, s.h);
+        try {
+            return new Cuda::Renderer(s, log);
+        } catch (std::exception &e) {
+            log->Info("Ray: Failed to create CUDA renderer, %s", e.what());
+        }
+    }
+    log->Error("Ray: no enabled renderer type is available in this library (only CUDA exists here; no CPU fallback)");
+    return nullptr;
+}
+
+namespace Cuda {
+
+Renderer::Renderer(const settings_t &s, ILog *log) : log_(log) {
+    int device = 0;
+    if (!s.preferred_device.empty()) {
+        device = atoi(std::string(s.preferred_device).c_str());
+    }
+    const int rc = rc_create(device, &ctx_);
+    if (rc != 0 || !ctx_) {
+        ctx_ = nullptr;
+        throw std::runtime_error("no usable sm_100 CUDA device (rc_create code " + std::to_string(rc) + ")");
+    }
+    device_name_ = rc_device_name(ctx_);
+    log_->Info("============================================================================");
+    log_->Info("Device       is %s", device_name_.c_str());
+    if (s.use_spatial_cache) {
+        log_->Warning("SpatialCache is not supported by the CUDA backend (ignored)");
+    }
+    log_->Info("============================================================================");
+    sampler_table_ = GenerateSamplerTable();
+    Resize(s.w, s.h);
+}
+
+Renderer::~Renderer() {
+    FreeMirrors();
+    if (ctx_) {
+        rc_destroy(ctx_);
+    }
+}
+
+void Renderer::FreeMirrors() {
+    rc_host_free(final_buf_);
+    rc_host_free(raw_buf_);
+    rc_host_free(base_color_buf_);
+    rc_host_free(depth_normals_buf_);
+    final_buf_ = raw_buf_ = base_color_buf_ = depth_normals_buf_ = nullptr;
+}
+
+void Renderer::Resize(const int w, const int h) {
+    if (w == w_ && h == h_) {
+        return;
+    }
+    if (rc_resize(ctx_, w, h) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+        return;
+    }
+    w_ = w;
+    h_ = h;
+    const size_t n = size_t(w) * h;
+    FreeMirrors();
+    final_buf_ = static_cast<color_rgba_t *>(rc_host_alloc(n * sizeof(color_rgba_t)));
+    raw_buf_ = static_cast<color_rgba_t *>(rc_host_alloc(n * sizeof(color_rgba_t)));
+    base_color_buf_ = static_cast<color_rgba_t *>(rc_host_alloc(n * sizeof(color_rgba_t)));
+    depth_normals_buf_ = static_cast<color_rgba_t *>(rc_host_alloc(n * sizeof(color_rgba_t)));
+    if (!final_buf_ || !raw_buf_ || !base_color_buf_ || !depth_normals_buf_) {
+        log_->Error("Ray(CUDA): failed to allocate the host pixel mirrors");
+        return;
+    }
+    memset(final_buf_, 0, n * sizeof(color_rgba_t));
+    memset(raw_buf_, 0, n * sizeof(color_rgba_t));
+    memset(base_color_buf_, 0, n * sizeof(color_rgba_t));
+    memset(depth_normals_buf_, 0, n * sizeof(color_rgba_t));
+    final_dirty_ = raw_dirty_ = base_dirty_ = dn_dirty_ = true;
+}
+
+void Renderer::Clear(const color_rgba_t &c) {
+    if (rc_clear(ctx_, c.v) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+    }
+}
+
+SceneBase *Renderer::CreateScene() { return new Scene(log_); }
+
+void Renderer::SetSamplerTable(const uint32_t *table) {
+    sampler_table_.assign(table, table + size_t(rt::kRandDims) * rt::kRandSamples * 2);
+    tables_dirty_ = true;
+}
+
+bool Renderer::Prepare(const Scene &s, const camera_t &cam) {
+    if (cam.rc.filter != filter_table_filter_ || cam.desc.filter_width != filter_table_width_) {
+        filter_table_ = GenerateFilterTable(cam.rc.filter, cam.desc.filter_width);
+        filter_table_filter_ = cam.rc.filter;
+        filter_table_width_ = cam.desc.filter_width;
+        tables_dirty_ = true;
+    }
+    if (tables_dirty_) {
+        if (rc_upload_tables(ctx_, sampler_table_.data(), rt::kRandDims, rt::kRandSamples, filter_table_.data(),
+                             int(filter_table_.size())) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+            return false;
+        }
+        tables_dirty_ = false;
+    }
+    if (uploaded_scene_ != &s || uploaded_revision_ != s.revision()) {
+        rc_scene_view v;
+        s.FillView(v);
+        if (rc_upload_scene(ctx_, &v) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+            return false;
+        }
+        uploaded_scene_ = &s;
+        uploaded_revision_ = s.revision();
+    }
+    return true;
+}
+
+void Renderer::RenderScene(const SceneBase &scene, RegionContext &region) { RenderSceneBatch(scene, region, 1); }
+
+void Renderer::RenderSceneBatch(const SceneBase &scene, RegionContext &region, const int count) {
+    const auto *sp = dynamic_cast<const Scene *>(&scene);
+    if (!sp) {
+        log_->Error("Ray(CUDA): RenderScene needs a scene created by this renderer's CreateScene()");
+        return;
+    }
+    const Scene &s = *sp;
+    std::shared_lock<std::shared_timed_mutex> lock(s.mtx_);
+    if (s.current_cam_._index >= s.cams_.size()) {
+        log_->Error("Ray(CUDA): the scene has no current camera");
+        return;
+    }
+    const camera_t &cam = s.cams_[s.current_cam_._index];
+    if (!Prepare(s, cam)) {
+        return;
+    }
+    rc_pass_desc p;
+    memset(&p, 0, sizeof(p));
+    p.cam = cam.rc;
+    p.rect = rc_rect{region.rect().x, region.rect().y, region.rect().w, region.rect().h};
+    p.flags = render_flags_ | RC_RENDER_ASYNC;
+    for (int i = 0; i < count; ++i) {
+        ++region.iteration;
+        p.iteration = region.iteration;
+        if (rc_render(ctx_, &p) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+            break;
+        }
+    }
+    if (rc_sync(ctx_) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+    }
+    final_dirty_ = raw_dirty_ = base_dirty_ = dn_dirty_ = true;
+}
+
+void Renderer::Readback(const int which, color_rgba_t *dst) const {
+    if (w_ == 0 || h_ == 0 || !dst) {
+        return;
+    }
+    const rc_rect r{0, 0, w_, h_};
+    if (rc_readback(ctx_, which, &r, &dst[0].v[0], w_) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+    }
+}
+
+color_data_rgba_t Renderer::get_pixels_ref() const {
+    if (final_dirty_) {
+        Readback(RC_BUF_FINAL, final_buf_);
+        final_dirty_ = false;
+    }
+    return {final_buf_, w_};
+}
+color_data_rgba_t Renderer::get_raw_pixels_ref() const {
+    if (raw_dirty_) {
+        Readback(RC_BUF_RAW, raw_buf_);
+        raw_dirty_ = false;
+    }
+    return {raw_buf_, w_};
+}
+color_data_rgba_t Renderer::get_aux_pixels_ref(const eAUXBuffer buf) const {
+    if (buf == eAUXBuffer::BaseColor) {
+        if (base_dirty_) {
+            Readback(RC_BUF_BASE_COLOR, base_color_buf_);
+            base_dirty_ = false;
+        }
+        return {base_color_buf_, w_};
+    } else if (buf == eAUXBuffer::DepthNormals) {
+        if (dn_dirty_) {
+            Readback(RC_BUF_DEPTH_NORMALS, depth_normals_buf_);
+            dn_dirty_ = false;
+        }
+        return {depth_normals_buf_, w_};
+    }
+    return {nullptr, 0};
+}
+
+// out of the hot-path scope: report through the log like any backend missing a feature
+void Renderer::DenoiseImage(const RegionContext &) { log_->Error("Ray(CUDA): NLM denoising is not implemented by the CUDA backend"); }
+void Renderer::DenoiseImage(int, const RegionContext &) { log_->Error("Ray(CUDA): UNet denoising is not implemented by the CUDA backend"); }
+void Renderer::UpdateSpatialCache(const SceneBase &, RegionContext &) { log_->Error("Ray(CUDA): the spatial cache is not implemented by the CUDA backend"); }
+void Renderer::ResolveSpatialCache(const SceneBase &, const ParallelFor &) { log_->Error("Ray(CUDA): the spatial cache is not implemented by the CUDA backend"); }
+void Renderer::ResetSpatialCache(const SceneBase &, const ParallelFor &) {}
+unet_filter_properties_t Renderer::InitUNetFilter(bool, const ParallelFor &) {
+    log_->Error("Ray(CUDA): the UNet filter is not implemented by the CUDA backend");
+    return {};
+}
+
+void Renderer::GetStats(stats_t &st) {
+    uint64_t us[11] = {};
+    rc_get_stats(ctx_, us);
+    st.time_primary_ray_gen_us = us[0];
+    st.time_primary_trace_us = us[1];
+    st.time_primary_shade_us = us[2];
+    st.time_primary_shadow_us = us[3];
+    st.time_secondary_sort_us = us[4];
+    st.time_secondary_trace_us = us[5];
+    st.time_secondary_shade_us = us[6];
+    st.time_secondary_shadow_us = us[7];
+    st.time_denoise_us = us[8];
+    st.time_cache_update_us = us[9];
+    st.time_cache_resolve_us = us[10];
+}
+void Renderer::ResetStats() { rc_reset_stats(ctx_); }
+
+} // namespace Cuda
+} // namespace RayB200

@@ -1,0 +1,86 @@
+// RendererCuda.h -- RayB200::Cuda::Renderer: the RendererBase implementation that drives libray_cuda.so.
+//
+// Role in the reference: the CUDA twin of Cpu::Renderer<SIMDPolicy> (internal/RendererCPU.h:193-320, RenderScene
+// :374-659) / Vk::Renderer (internal/RendererVK.cpp:368-791).  All device work goes through the C-ABI of
+// include/ray_cuda.h; this class only converts arguments, tracks scene revisions, and keeps host mirrors of the
+// frame buffers for get_*_pixels_ref (lazy readback with dirty flags, like RendererVK.cpp:1698-1757).
+#pragma once
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/ray_cuda.h"
+#include "RayB200.h"
+#include "SceneCuda.h"
+
+namespace RayB200 {
+namespace Cuda {
+
+class Renderer final : public RendererBase {
+    ILog *log_;
+    rc_ctx *ctx_ = nullptr;
+    int w_ = 0, h_ = 0;
+    std::string device_name_;
+
+    // host mirrors of the device planes, in pinned memory (rc_host_alloc) so a readback runs at full PCIe speed
+    mutable color_rgba_t *final_buf_ = nullptr, *raw_buf_ = nullptr, *base_color_buf_ = nullptr, *depth_normals_buf_ = nullptr;
+    mutable bool final_dirty_ = true, raw_dirty_ = true, base_dirty_ = true, dn_dirty_ = true;
+
+    const Scene *uploaded_scene_ = nullptr;
+    uint64_t uploaded_revision_ = 0;
+    uint32_t filter_table_filter_ = 0xffffffffu;
+    float filter_table_width_ = 0.0f;
+    std::vector<uint32_t> sampler_table_;
+    bool tables_dirty_ = true;
+    std::vector<float> filter_table_;
+    uint32_t render_flags_ = 0;
+
+    void Readback(int which, color_rgba_t *dst) const;
+    void FreeMirrors();
+    bool Prepare(const Scene &s, const camera_t &cam);
+
+  public:
+    Renderer(const settings_t &s, ILog *log); // throws std::runtime_error when no sm_100 device can be opened
+    ~Renderer() override;
+
+    eRendererType type() const override { return eRendererType::CUDA; }
+    ILog *log() const override { return log_; }
+    std::string_view device_name() const override { return device_name_; }
+    std::pair<int, int> size() const override { return {w_, h_}; }
+    color_data_rgba_t get_pixels_ref() const override;
+    color_data_rgba_t get_raw_pixels_ref() const override;
+    color_data_rgba_t get_aux_pixels_ref(eAUXBuffer buf) const override;
+    const shl1_data_t *get_sh_data_ref() const override { return nullptr; }
+    void Resize(int w, int h) override;
+    void Clear(const color_rgba_t &c) override;
+    SceneBase *CreateScene() override;
+    void RenderScene(const SceneBase &scene, RegionContext &region) override;
+    void DenoiseImage(const RegionContext &region) override;
+    void DenoiseImage(int pass, const RegionContext &region) override;
+    void UpdateSpatialCache(const SceneBase &scene, RegionContext &region) override;
+    void ResolveSpatialCache(const SceneBase &scene, const ParallelFor &parallel_for) override;
+    void ResetSpatialCache(const SceneBase &scene, const ParallelFor &parallel_for) override;
+    void GetStats(stats_t &st) override;
+    void ResetStats() override;
+    unet_filter_properties_t InitUNetFilter(bool alias_memory, const ParallelFor &parallel_for) override;
+
+    // ---- CUDA-backend extras (not part of RendererBase) ----
+    /// `count` consecutive RenderScene calls on the same region enqueued back to back with ONE synchronisation at the
+    /// end (the per-call blocking semantic of RenderScene costs a host round trip per sample).
+    void RenderSceneBatch(const SceneBase &scene, RegionContext &region, int count);
+    /// Replace the built-in (0,2)-sequence sampler table with a caller-provided 32 x 4096 x 2 table -- inside the
+    /// reference tree this is `__pmj02_samples`; parity tests pass that table so the sample sequences are identical.
+    void SetSamplerTable(const uint32_t *table);
+    void SetRenderFlags(uint32_t rc_render_flags) { render_flags_ = rc_render_flags; }
+    /// Forget the uploaded scene: the next RenderScene copies all scene arrays host->device again (dynamic scenes,
+    /// end-to-end measurements).
+    void InvalidateScene() { uploaded_scene_ = nullptr; }
+    rc_ctx *native_context() const { return ctx_; }
+};
+
+std::vector<uint32_t> GenerateSamplerTable();                                   // SamplerTable.cpp
+std::vector<float> GenerateFilterTable(uint32_t filter, float filter_width);   // FilterTable.cpp
+
+} // namespace Cuda
+} // namespace RayB200

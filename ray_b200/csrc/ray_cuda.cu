@@ -66,6 +66,7 @@ struct rc_ctx {
 
     bool stats_enabled = true;
     std::vector<cudaEvent_t> events;
+    cudaEvent_t user_events[8] = {};
     struct PendingSample {
         int max_bounces;
     };
@@ -576,6 +577,9 @@ int rc_create(int device, rc_ctx **out_ctx) {
     for (auto &e : ctx->events) {
         cudaEventCreate(&e);
     }
+    for (auto &e : ctx->user_events) {
+        cudaEventCreate(&e);
+    }
     if (dev_alloc(ctx, &ctx->d_counters, CNT_TOTAL) || dev_alloc(ctx, &ctx->d_totals, TOT_COUNT)) {
         rc_destroy(ctx);
         return 6;
@@ -602,6 +606,9 @@ void rc_destroy(rc_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream);
     }
     for (auto &e : ctx->events) {
+        cudaEventDestroy(e);
+    }
+    for (auto &e : ctx->user_events) {
         cudaEventDestroy(e);
     }
     cudaFree(ctx->fb.temp);
@@ -1108,6 +1115,56 @@ int rc_stage_sort_rays(rc_ctx *ctx, void *rays, int count, uint32_t *hashes_out)
         CU_CHECK(ctx, cudaMemcpy(hashes_out, ctx->sort.keys_sorted, size_t(count) * sizeof(uint32_t),
                                  cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+void *rc_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void rc_host_free(void *p) {
+    if (p) {
+        cudaFreeHost(p);
+    }
+}
+
+void *rc_device_ptr(rc_ctx *ctx, int which) {
+    if (!ctx) {
+        return nullptr;
+    }
+    switch (which) {
+    case RC_BUF_FINAL: return ctx->fb.final;
+    case RC_BUF_RAW: return ctx->fb.raw;
+    case RC_BUF_BASE_COLOR: return ctx->fb.base_color;
+    case RC_BUF_DEPTH_NORMALS: return ctx->fb.depth_normals;
+    case RC_BUF_FULL: return ctx->fb.full;
+    case RC_BUF_HALF: return ctx->fb.half;
+    case RC_BUF_TEMP: return ctx->fb.temp;
+    default: return nullptr;
+    }
+}
+
+int rc_event_record(rc_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) {
+        return fail(ctx, "rc_event_record: bad slot");
+    }
+    cudaSetDevice(ctx->device);
+    CU_CHECK(ctx, cudaEventRecord(ctx->user_events[slot], ctx->stream));
+    return 0;
+}
+
+int rc_event_elapsed_ms(rc_ctx *ctx, int a, int b, float *ms) {
+    if (!ctx || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) {
+        return fail(ctx, "rc_event_elapsed_ms: bad argument");
+    }
+    cudaSetDevice(ctx->device);
+    CU_CHECK(ctx, cudaEventSynchronize(ctx->user_events[b]));
+    CU_CHECK(ctx, cudaEventElapsedTime(ms, ctx->user_events[a], ctx->user_events[b]));
     return 0;
 }
 

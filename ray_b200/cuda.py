@@ -60,6 +60,11 @@ def load_library():
         "rc_stage_sort_rays": (C.c_int, [vp, vp, C.c_int, vp]),
         "rc_debug_fill_temp": (C.c_int, [vp, P(C.c_float)]),
         "rc_abi_sizeof": (C.c_int, [C.c_int]),
+        "rc_host_alloc": (vp, [C.c_size_t]),
+        "rc_host_free": (None, [vp]),
+        "rc_device_ptr": (vp, [vp, C.c_int]),
+        "rc_event_record": (C.c_int, [vp, C.c_int]),
+        "rc_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, P(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not export what include/ray_cuda.h declares
@@ -74,7 +79,8 @@ EXPORTED_SYMBOLS = [
     "rc_upload_tables", "rc_upload_scene", "rc_render", "rc_sync", "rc_readback", "rc_readback_required_samples",
     "rc_enable_stats", "rc_get_stats", "rc_get_counters", "rc_reset_stats", "rc_get_kernel_ms",
     "rc_stage_generate_primary_rays", "rc_stage_trace_rays", "rc_stage_shade", "rc_stage_trace_shadow_rays",
-    "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof",
+    "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
+    "rc_event_record", "rc_event_elapsed_ms",
 ]
 
 
