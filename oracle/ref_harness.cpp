@@ -662,4 +662,119 @@ void ro_stage_trace_shadow_rays(ro_scene *s, int w, int iteration, const void *s
                          rand_seed_for(iteration), iteration, sc->textures(), w, reinterpret_cast<color_rgba_t *>(temp));
 }
 
+// ---- the same Ref:: stage functions over CALLER-PROVIDED scene arrays (an rc_scene_view) ---------------------------
+// Lets a CPU test run the reference's own traversal / shading code over the arrays produced by the product's host layer
+// (ray_b200/csrc/host: its own BVH8, triangle blocks, light tree), i.e. validate those builders without a GPU.
+namespace {
+struct ViewScene {
+    environment_t env = {};
+    cache_grid_params_t cache_grid;
+    const Cpu::TexStorageBase *textures[8] = {};
+    std::vector<uint32_t> dir_lights;
+
+    scene_data_t make(const rc_scene_view &v) {
+        memcpy(env.env_col, v.env_col, sizeof(env.env_col));
+        env.env_map = v.env_map;
+        memcpy(env.back_col, v.back_col, sizeof(env.back_col));
+        env.back_map = v.back_map;
+        env.qtree_levels = 0;
+        env.importance_sample = true;
+        env.light_index = v.env_light_index;
+        env.sky_map_spread_angle = v.sky_map_spread_angle;
+        return scene_data_t{env,
+                            static_cast<const mesh_instance_t *>(v.mesh_instances.ptr),
+                            nullptr,
+                            static_cast<const uint32_t *>(v.vtx_indices.ptr),
+                            static_cast<const vertex_t *>(v.vertices.ptr),
+                            nullptr,
+                            static_cast<const wbvh_node_t *>(v.wnodes.ptr),
+                            nullptr,
+                            static_cast<const uint32_t *>(v.tri_indices.ptr),
+                            static_cast<const mtri_accel_t *>(v.mtris.ptr),
+                            static_cast<const tri_mat_data_t *>(v.tri_materials.ptr),
+                            static_cast<const material_t *>(v.materials.ptr),
+                            {static_cast<const light_t *>(v.lights.ptr), v.lights.count},
+                            {static_cast<const uint32_t *>(v.li_indices.ptr), v.li_indices.count},
+                            {dir_lights},
+                            v.visible_lights_count,
+                            v.blocker_lights_count,
+                            {},
+                            {static_cast<const light_cwbvh_node_t *>(v.light_cwnodes.ptr), v.light_cwnodes.count},
+                            {},
+                            {},
+                            cache_grid,
+                            {},
+                            {}};
+    }
+};
+
+pass_settings_t pass_from(const rc_camera &c) {
+    pass_settings_t ps = {};
+    ps.max_diff_depth = uint8_t(c.max_diff_depth);
+    ps.max_spec_depth = uint8_t(c.max_spec_depth);
+    ps.max_refr_depth = uint8_t(c.max_refr_depth);
+    ps.max_transp_depth = uint8_t(c.max_transp_depth);
+    ps.max_total_depth = uint8_t(c.max_total_depth);
+    ps.min_total_depth = uint8_t(c.min_total_depth);
+    ps.min_transp_depth = uint8_t(c.min_transp_depth);
+    ps.clamp_direct = c.clamp_direct;
+    ps.clamp_indirect = c.clamp_indirect;
+    ps.min_samples = c.min_samples;
+    ps.variance_threshold = c.variance_threshold;
+    ps.regularize_alpha = c.regularize_alpha;
+    return ps;
+}
+} // namespace
+
+void ro_view_trace_rays(const rc_scene_view *v, const rc_camera *cam, int iteration, void *rays, void *hits, int count,
+                        int trace_lights) {
+    ViewScene vs;
+    const scene_data_t sd = vs.make(*v);
+    if (v->tlas_root == 0xffffffff) {
+        return;
+    }
+    Ref::TraceRays(Span<Ref::ray_data_t>{static_cast<Ref::ray_data_t *>(rays), count}, int(cam->min_transp_depth),
+                   int(cam->max_transp_depth), sd, v->tlas_root, trace_lights != 0, vs.textures, __pmj02_samples,
+                   rand_seed_for(iteration), iteration, Span<Ref::hit_data_t>{static_cast<Ref::hit_data_t *>(hits), count});
+}
+
+void ro_view_shade(const rc_scene_view *v, const rc_camera *cam, int w, int h, int iteration, int primary, int bounce,
+                   const void *rays, const void *hits, int count, void *secondary_out, int *secondary_count,
+                   void *shadow_out, int *shadow_count, float *temp, float *base_color, float *depth_normals) {
+    ViewScene vs;
+    const scene_data_t sd = vs.make(*v);
+    const pass_settings_t ps = pass_from(*cam);
+    std::vector<uint32_t> def_sky(size_t(count) + 1);
+    int def_sky_count = 0;
+    *secondary_count = *shadow_count = 0;
+    const Span<const Ref::hit_data_t> hs{static_cast<const Ref::hit_data_t *>(hits), count};
+    const Span<const Ref::ray_data_t> rs{static_cast<const Ref::ray_data_t *>(rays), count};
+    if (primary) {
+        Ref::ShadePrimary(ps, hs, rs, __pmj02_samples, rand_seed_for(iteration), iteration, eSpatialCacheMode::None, sd,
+                          vs.textures, static_cast<Ref::ray_data_t *>(secondary_out), secondary_count,
+                          static_cast<Ref::shadow_ray_t *>(shadow_out), shadow_count, def_sky.data(), &def_sky_count, w,
+                          1.0f / float(iteration), reinterpret_cast<color_rgba_t *>(temp),
+                          reinterpret_cast<color_rgba_t *>(base_color), reinterpret_cast<color_rgba_t *>(depth_normals));
+    } else {
+        const float clamp_direct = (bounce == 1) ? ps.clamp_direct : ps.clamp_indirect;
+        Ref::ShadeSecondary(ps, clamp_direct, hs, rs, __pmj02_samples, rand_seed_for(iteration), iteration,
+                            eSpatialCacheMode::None, sd, vs.textures, static_cast<Ref::ray_data_t *>(secondary_out),
+                            secondary_count, static_cast<Ref::shadow_ray_t *>(shadow_out), shadow_count, def_sky.data(),
+                            &def_sky_count, w, reinterpret_cast<color_rgba_t *>(temp), nullptr, nullptr);
+    }
+    (void)h;
+}
+
+void ro_view_trace_shadow_rays(const rc_scene_view *v, const rc_camera *cam, int w, int iteration,
+                               const void *shadow_rays, int count, float clamp_val, float *temp) {
+    ViewScene vs;
+    const scene_data_t sd = vs.make(*v);
+    if (v->tlas_root == 0xffffffff) {
+        return;
+    }
+    Ref::TraceShadowRays(Span<const Ref::shadow_ray_t>{static_cast<const Ref::shadow_ray_t *>(shadow_rays), count},
+                         int(cam->max_transp_depth), clamp_val, sd, v->tlas_root, __pmj02_samples,
+                         rand_seed_for(iteration), iteration, vs.textures, w, reinterpret_cast<color_rgba_t *>(temp));
+}
+
 } // extern "C"

@@ -64,6 +64,11 @@ def load():
         "ro_stage_shade": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, P(C.c_int), vp,
                                   P(C.c_int), vp, vp, vp]),
         "ro_stage_trace_shadow_rays": (None, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_float, vp]),
+        "ro_view_trace_rays": (None, [P(capi.rc_scene_view), P(capi.rc_camera), C.c_int, vp, vp, C.c_int, C.c_int]),
+        "ro_view_shade": (None, [P(capi.rc_scene_view), P(capi.rc_camera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 vp, vp, C.c_int, vp, P(C.c_int), vp, P(C.c_int), vp, vp, vp]),
+        "ro_view_trace_shadow_rays": (None, [P(capi.rc_scene_view), P(capi.rc_camera), C.c_int, C.c_int, vp, C.c_int,
+                                             C.c_float, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -203,6 +208,71 @@ class Scene:
         shadow_rays = np.ascontiguousarray(shadow_rays)
         self.lib.ro_stage_trace_shadow_rays(self.h, w, iteration, _ptr(shadow_rays), len(shadow_rays),
                                             float(clamp_val), _ptr(temp))
+
+
+class ViewScene:
+    """The reference's Ref:: stage functions run over CALLER-PROVIDED scene arrays (an rc_scene_view + rc_camera), e.g.
+    the arrays built by the product's host layer: validates those builders with the reference's own code, on CPU."""
+
+    def __init__(self, view, cam):
+        self.lib = load()
+        self.view, self.cam = view, cam
+
+    def trace_rays(self, iteration, rays, hits, trace_lights):
+        rays = np.ascontiguousarray(rays.copy())
+        hits = np.ascontiguousarray(hits.copy())
+        self.lib.ro_view_trace_rays(C.byref(self.view), C.byref(self.cam), iteration, _ptr(rays), _ptr(hits), len(rays),
+                                    1 if trace_lights else 0)
+        return rays, hits
+
+    def shade(self, w, h, iteration, primary, bounce, rays, hits, temp, base_color=None, depth_normals=None):
+        rays = np.ascontiguousarray(rays)
+        hits = np.ascontiguousarray(hits)
+        n = len(rays)
+        sec = np.zeros(n + 1, dtype=RAY_DTYPE)
+        sh = np.zeros(n + 1, dtype=SHADOW_DTYPE)
+        ns, nh = C.c_int(0), C.c_int(0)
+        base_color = np.zeros((h, w, 4), np.float32) if base_color is None else base_color
+        depth_normals = np.zeros((h, w, 4), np.float32) if depth_normals is None else depth_normals
+        self.lib.ro_view_shade(C.byref(self.view), C.byref(self.cam), w, h, iteration, 1 if primary else 0, bounce,
+                               _ptr(rays), _ptr(hits), n, _ptr(sec), C.byref(ns), _ptr(sh), C.byref(nh), _ptr(temp),
+                               _ptr(base_color), _ptr(depth_normals))
+        return sec[:ns.value].copy(), sh[:nh.value].copy(), base_color, depth_normals
+
+    def trace_shadow_rays(self, w, iteration, shadow_rays, clamp_val, temp):
+        shadow_rays = np.ascontiguousarray(shadow_rays)
+        self.lib.ro_view_trace_shadow_rays(C.byref(self.view), C.byref(self.cam), w, iteration, _ptr(shadow_rays),
+                                           len(shadow_rays), float(clamp_val), _ptr(temp))
+
+
+def render_with_stages(sc, gen_scene, w, h, spp, max_bounces=8):
+    """One full RenderScene sequence per sample (primary + bounces) through stage functions of `sc` (a Scene or a
+    ViewScene); primary rays come from `gen_scene` (a Scene: ray generation only needs the camera). Returns the mean
+    radiance image (h, w, 4) and the number of closest-hit rays traced."""
+    acc = np.zeros((h, w, 4), np.float64)
+    n_rays = 0
+    cam = gen_scene.camera()
+    for it in range(1, spp + 1):
+        temp = np.zeros((h, w, 4), np.float32)
+        rays, hits = gen_scene.generate_primary_rays(w, h, (0, 0, w, h), it)
+        rays, hits = sc.trace_rays(it, rays, hits, False)
+        n_rays += len(rays)
+        sec, sh, _, _ = sc.shade(w, h, it, True, 0, rays, hits, temp)
+        sc.trace_shadow_rays(w, it, sh, cam.clamp_direct, temp)
+        for bounce in range(1, min(max_bounces, cam.max_total_depth) + 1):
+            if len(sec) == 0:
+                break
+            hits0 = np.zeros(len(sec), dtype=HIT_DTYPE)
+            hits0["obj_index"] = -1
+            hits0["prim_index"] = -1
+            hits0["t"] = np.float32(3.402823466e+30)
+            hits0["v"] = -1.0
+            n_rays += len(sec)
+            r2, h2 = sc.trace_rays(it, sec, hits0, True)
+            sec, sh, _, _ = sc.shade(w, h, it, False, bounce, r2, h2, temp)
+            sc.trace_shadow_rays(w, it, sh, cam.clamp_indirect, temp)
+        acc += temp
+    return (acc / spp).astype(np.float32), n_rays
 
 
 class Renderer:
