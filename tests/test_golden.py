@@ -119,7 +119,7 @@ def test_cuda_trace_reproduces_golden_without_the_oracle(path):
     w, h = [int(x) for x in g["wh"]]
     ctx = cuda.Context(0)
     ctx.resize(w, h)
-    ctx.upload_tables(np.zeros(32 * 4096 * 2, np.uint32))
+    ctx.upload_tables(np.zeros(32 * 4096 * 2, np.uint32), g["filter_table"])
     ctx.upload_scene(v)
     cam = capi.rc_camera.from_buffer_copy(g["cam"].tobytes())
     p = ctx.make_pass(cam, (0, 0, w, h), int(g["iteration"]))
@@ -148,7 +148,7 @@ def test_cuda_shading_and_image_reproduce_golden(path, oracle_mod):
     it = int(g["iteration"])
     ctx = cuda.Context(0)
     ctx.resize(w, h)
-    ctx.upload_tables(oracle_mod.pmj_table())
+    ctx.upload_tables(oracle_mod.pmj_table(), g["filter_table"])
     ctx.upload_scene(v)
     cam = capi.rc_camera.from_buffer_copy(g["cam"].tobytes())
     p = ctx.make_pass(cam, (0, 0, w, h), it)

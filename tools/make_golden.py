@@ -51,6 +51,7 @@ def make(name, desc, iteration=2, spp=4):
     d = view_to_dict(sc.view())
     d["cam"] = np.frombuffer(bytes(cam), np.uint8).copy()
     d["wh"] = np.asarray([w, h], np.int32)
+    d["filter_table"] = sc.filter_table()  # reference UpdateFilterTable output for cam.filter / cam.fwidth
     d["iteration"] = np.int32(iteration)
     rays, hits = sc.generate_primary_rays(w, h, (0, 0, w, h), iteration)
     d["primary_rays"], d["primary_hits_in"] = rays, hits
