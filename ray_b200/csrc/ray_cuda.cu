@@ -345,8 +345,8 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     ctx->kernel_launches[KF_RAYGEN]++;
     record(ctx, EV_RAYGEN);
 
-    const int trace_grid = persistent_grid(ctx, 8);
-    const int shade_grid = persistent_grid(ctx, 4);
+    const int trace_grid = persistent_grid(ctx, RT_TRACE_BLOCKS);
+    const int shade_grid = persistent_grid(ctx, RT_SHADE_BLOCKS);
     const bool have_geo = ctx->scene_info.tlas_root != 0xffffffffu;
 
     if (have_geo) {
@@ -358,7 +358,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     const float mix_factor = 1.0f / float(p.iteration);
     {
         const float lim = clamp_limit(p.ps.clamp_direct);
-        k_shade<true><<<shade_grid, 128, 0, s>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
+        k_shade<true><<<shade_grid, RT_SHADE_THREADS, 0, s>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
                                                   mix_factor);
         ctx->kernel_launches[KF_SHADE]++;
     }
@@ -392,7 +392,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
         record(ctx, e + 1);
         {
             const float cd = (bounce == 1) ? p.ps.clamp_direct : p.ps.clamp_indirect;
-            k_shade<false><<<shade_grid, 128, 0, s>>>(p, ctx->rays[cur], ctx->hits, ctx->rays[cur ^ 1], ctx->shadow,
+            k_shade<false><<<shade_grid, RT_SHADE_THREADS, 0, s>>>(p, ctx->rays[cur], ctx->hits, ctx->rays[cur ^ 1], ctx->shadow,
                                                        bounce, clamp_limit(cd), clamp_limit(p.ps.clamp_indirect),
                                                        mix_factor);
             ctx->kernel_launches[KF_SHADE]++;
@@ -985,7 +985,7 @@ int rc_stage_trace_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays, void 
         set_counter(ctx, CNT_RAYS + 0, uint32_t(count))) {
         return 1;
     }
-    const int grid = persistent_grid(ctx, 8);
+    const int grid = persistent_grid(ctx, RT_TRACE_BLOCKS);
     if (ctx->scene_info.tlas_root != 0xffffffffu) {
         if (trace_lights && ctx->scene_info.visible_lights_count != 0) {
             k_trace_closest<true, false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0);
@@ -1024,15 +1024,15 @@ int rc_stage_shade(rc_ctx *ctx, const rc_pass_desc *pass, int primary, int bounc
         set_counter(ctx, CNT_RAYS + 0, uint32_t(count))) {
         return 1;
     }
-    const int grid = persistent_grid(ctx, 4);
+    const int grid = persistent_grid(ctx, RT_SHADE_BLOCKS);
     const float mix_factor = 1.0f / float(p.iteration);
     if (primary) {
         const float lim = clamp_limit(p.ps.clamp_direct);
-        k_shade<true><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
+        k_shade<true><<<grid, RT_SHADE_THREADS, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
                                                       mix_factor);
     } else {
         const float cd = (bounce == 1) ? p.ps.clamp_direct : p.ps.clamp_indirect;
-        k_shade<false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0,
+        k_shade<false><<<grid, RT_SHADE_THREADS, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0,
                                                        clamp_limit(cd), clamp_limit(p.ps.clamp_indirect), mix_factor);
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1075,7 +1075,7 @@ int rc_stage_trace_shadow_rays(rc_ctx *ctx, const rc_pass_desc *pass, const void
         return 1;
     }
     if (ctx->scene_info.tlas_root != 0xffffffffu) {
-        k_trace_shadow<<<persistent_grid(ctx, 8), 128, 0, ctx->stream>>>(p, ctx->shadow, 0, clamp_limit(clamp_val));
+        k_trace_shadow<<<persistent_grid(ctx, RT_TRACE_BLOCKS), 128, 0, ctx->stream>>>(p, ctx->shadow, 0, clamp_limit(clamp_val));
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaGetLastError());

@@ -13,6 +13,24 @@
 
 #include "rt_shade.cuh"
 
+// Launch shapes of the persistent kernels (measured on hall-250k, profiles/README.md "launch shape sweep"):
+//  * k_shade is instruction-FETCH bound (177 KB of straight-line SASS walked once per ray, I-cache hit rate 65 %):
+//    big blocks whose warps are re-aligned with __syncthreads() between the phases walk the same cache lines together
+//    (119 -> 82 ms per 16 samples); 64 registers / thread costs spills but doubles the resident warps.
+//  * the trace kernels want 6 resident 128-thread blocks (80 registers): 96 -> 88 ms closest, 102 -> 89 ms shadow.
+#ifndef RT_SHADE_THREADS
+#define RT_SHADE_THREADS 512
+#endif
+#ifndef RT_SHADE_BLOCKS
+#define RT_SHADE_BLOCKS 2
+#endif
+#ifndef RT_SHADE_SYNC
+#define RT_SHADE_SYNC 1
+#endif
+#ifndef RT_TRACE_BLOCKS
+#define RT_TRACE_BLOCKS 6
+#endif
+
 namespace rt {
 
 struct RayBuf {
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(256) k_raygen(KParams p, RayBuf rays, HitBuf h
 // INIT_HITS: secondary lists start from the default "no intersection" record (RendererCPU.h:532-535) built in
 // registers instead of a memset pass + 20 B/ray read.
 template <bool TRACE_LIGHTS, bool INIT_HITS>
-__global__ void __launch_bounds__(128) k_trace_closest(KParams p, RayBuf rays, HitBuf hits, int bounce) {
+__global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_closest(KParams p, RayBuf rays, HitBuf hits, int bounce) {
     const uint32_t count = p.counters[CNT_RAYS + bounce];
     uint32_t *head = &p.counters[CNT_HEAD_TRACE + bounce];
     const int lane = threadIdx.x & 31;
@@ -382,25 +400,46 @@ __global__ void __launch_bounds__(128) k_trace_closest(KParams p, RayBuf rays, H
 // ---- ShadePrimary / ShadeSecondary (ShadeRef.cpp:1654-1737) --------------------------------------------------------
 // `bounce` = index of the ray list being shaded (0 = primary).  Secondary rays go to list bounce+1.
 template <bool PRIMARY>
-__global__ void __launch_bounds__(128, 4) k_shade(KParams p, RayBuf rays, HitBuf hits, RayBuf out_rays, ShadowBuf out_shadow,
-                                               int bounce, float limit0, float limit1, float mix_factor) {
+__global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS)
+    k_shade(KParams p, RayBuf rays, HitBuf hits, RayBuf out_rays, ShadowBuf out_shadow, int bounce, float limit0,
+            float limit1, float mix_factor) {
     const uint32_t count = p.counters[CNT_RAYS + bounce];
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t tl_stack[kMaxStack];
     float tl_factors[kMaxStack];
-    for (uint32_t base = warp_id * 32; base < count; base += num_warps * 32) {
-        const uint32_t i = base + lane;
+    // block-uniform trip count, so the warps of a block can be kept in step (RT_SHADE_SYNC): the shading code is a
+    // long straight line walked once per ray, and warps that walk it together share instruction-cache lines
+    for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+#if RT_SHADE_SYNC
+        __syncthreads();
+#endif
+        const uint32_t i = base + threadIdx.x;
         const bool valid = i < count;
         ShadeOut out;
         out.has_secondary = out.has_shadow = false;
         uint32_t xy = 0;
+        RayD ray;
+        Hit inter;
+        MatCtx c;
+        bool more = false;
         if (valid) {
-            const RayD ray = load_ray(rays, i);
-            const Hit inter = load_hit(hits, i);
+            ray = load_ray(rays, i);
+            inter = load_hit(hits, i);
             xy = ray.xy;
-            shade_surface(p.ps, limit0, limit1, inter, ray, p.rand_seed, p.iteration, p.sc, tl_stack, tl_factors, out);
+            more = shade_surface_a(p.ps, limit0, inter, ray, p.rand_seed, p.iteration, p.sc, tl_stack, tl_factors, c, out);
+        }
+#if RT_SHADE_SYNC
+        __syncthreads();
+#endif
+        if (more) {
+            shade_surface_l(c);
+        }
+#if RT_SHADE_SYNC
+        __syncthreads();
+#endif
+        if (more) {
+            shade_surface_b(c, limit1, out);
+        }
+        if (valid) {
             const int x = int((xy >> 16) & 0xffff), y = int(xy & 0xffff);
             const int pix = y * p.fb.w + x;
             if (PRIMARY) {
@@ -456,7 +495,7 @@ __global__ void k_init_hits(KParams p, HitBuf hits, int bounce) {
 }
 
 // ---- TraceShadowRays (CoreRef.cpp:4856-4882) + IntersectScene(shadow) (:3160-3262) -------------------------------
-__global__ void __launch_bounds__(128) k_trace_shadow(KParams p, ShadowBuf srays, int stage, float limit) {
+__global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_shadow(KParams p, ShadowBuf srays, int stage, float limit) {
     const uint32_t count = p.counters[CNT_SHADOW + stage];
     uint32_t *head = &p.counters[CNT_HEAD_SHADOW + stage];
     const int lane = threadIdx.x & 31;

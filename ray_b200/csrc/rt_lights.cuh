@@ -131,6 +131,92 @@ RT_FN void lnode_importance(const LightCWNode &n, const float bmin[24], const fl
     }
 }
 
+// calc_lnode_importance straight from the quantised node: the child's box is decoded where it is used, so the 48
+// decoded bounds never exist as (local-memory) arrays.  Same operations per child as unpack_cw_bounds +
+// lnode_importance above.
+RT_FN void lnode_importance_q(const LightCWNode &n, v3 P, float imp[8]) {
+    const float bm0 = n.bbox_min[0], bm1 = n.bbox_min[1], bm2 = n.bbox_min[2];
+    const float ext0 = (n.bbox_max[0] - bm0) / 255.0f, ext1 = (n.bbox_max[1] - bm1) / 255.0f,
+                ext2 = (n.bbox_max[2] - bm2) / 255.0f;
+    // 6 rows of 8 quantised bytes
+    const uint2 *q = reinterpret_cast<const uint2 *>(&n.ch_bbox_min[0][0]);
+    const uint2 qmin0 = q[0], qmin1 = q[1], qmin2 = q[2], qmax0 = q[3], qmax1 = q[4], qmax2 = q[5];
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        float v = n.flux[i];
+        const int sh = (i & 3) * 8;
+        const bool hi = i >= 4;
+        const uint32_t cmin0 = ((hi ? qmin0.y : qmin0.x) >> sh) & 0xffu, cmax0 = ((hi ? qmax0.y : qmax0.x) >> sh) & 0xffu;
+        // (an "empty" child -- min 0xff / max 0 on axis 0 -- decodes to a box at -/+MAX_DIST and is skipped below)
+        if (v != 0.0f && (cmin0 != 0xffu || cmax0 != 0u)) {
+            const uint32_t cmin1 = ((hi ? qmin1.y : qmin1.x) >> sh) & 0xffu, cmin2 = ((hi ? qmin2.y : qmin2.x) >> sh) & 0xffu,
+                           cmax1 = ((hi ? qmax1.y : qmax1.x) >> sh) & 0xffu, cmax2 = ((hi ? qmax2.y : qmax2.x) >> sh) & 0xffu;
+            const float bmin0 = bm0 + float(cmin0) * ext0, bmin1 = bm1 + float(cmin1) * ext1, bmin2 = bm2 + float(cmin2) * ext2;
+            const float bmax0 = bm0 + float(cmax0) * ext0, bmax1 = bm1 + float(cmax1) * ext1, bmax2 = bm2 + float(cmax2) * ext2;
+            if (bmin0 > -kMaxDist) {
+                // decode_oct_dir (vector form)
+                const uint32_t oct = n.axis[i];
+                float a0 = -1.0f + 2.0f * float((oct >> 16) & 0xffffu) / 65535.0f;
+                float a1 = -1.0f + 2.0f * float(oct & 0xffffu) / 65535.0f;
+                float a2 = 1.0f - sse_abs(a0) - sse_abs(a1);
+                if (a2 < 0.0f) {
+                    const float temp = a0;
+                    a0 = (1.0f - sse_abs(a1)) * copysignf(1.0f, temp);
+                    a1 = (1.0f - sse_abs(temp)) * copysignf(1.0f, a1);
+                }
+                const float al = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+                a0 = a0 / al;
+                a1 = a1 / al;
+                a2 = a2 / al;
+
+                const float e0 = bmax0 - bmin0, e1 = bmax1 - bmin1, e2 = bmax2 - bmin2;
+                const float extent = 0.5f * sqrtf(e0 * e0 + e1 * e1 + e2 * e2);
+
+                const float pc0 = 0.5f * (bmin0 + bmax0), pc1 = 0.5f * (bmin1 + bmax1), pc2 = 0.5f * (bmin2 + bmax2);
+                float w0 = P.x - pc0, w1 = P.y - pc1, w2 = P.z - pc2;
+                const float dist2 = w0 * w0 + w1 * w1 + w2 * w2;
+                const float dist = sqrtf(dist2);
+                w0 /= dist;
+                w1 /= dist;
+                w2 /= dist;
+
+                const float v_len2 = sse_max(dist2, extent);
+
+                const float cos_omega_w = a0 * w0 + a1 * w1 + a2 * w2;
+                const float sin_omega_w = sqrtf(sse_max(1.0f - cos_omega_w * cos_omega_w, 0.0f));
+
+                float cos_omega_b = sqrtf(sse_max(1.0f - (extent * extent) / dist2, 0.0f));
+                if (dist2 < extent * extent) {
+                    cos_omega_b = -1.0f;
+                }
+                const float sin_omega_b = sqrtf(1.0f - cos_omega_b * cos_omega_b);
+
+                const uint32_t cv = n.cos_omega_ne[i];
+                const float cos_omega_n = 2.0f * (float((cv >> 16) & 0xffffu) / 65534.0f) - 1.0f;
+                const float cos_omega_e = 2.0f * (float(cv & 0xffffu) / 65534.0f) - 1.0f;
+                const float sin_omega_n = sqrtf(1.0f - cos_omega_n * cos_omega_n);
+
+                float cos_omega_x = cos_omega_w * cos_omega_n + sin_omega_w * sin_omega_n;
+                float sin_omega_x = sin_omega_w * cos_omega_n - cos_omega_w * sin_omega_n;
+                if (cos_omega_w > cos_omega_n) {
+                    cos_omega_x = 1.0f;
+                    sin_omega_x = 0.0f;
+                }
+                float cos_omega = cos_omega_x * cos_omega_b + sin_omega_x * sin_omega_b;
+                if (cos_omega_x > cos_omega_b) {
+                    cos_omega = 1.0f;
+                }
+                float mul = 0.0f;
+                if (cos_omega > cos_omega_e) {
+                    mul = cos_omega / v_len2;
+                }
+                v = v * mul;
+            }
+        }
+        imp[i] = v;
+    }
+}
+
 // hsum(imp[0..3] + imp[4..7]) with the SSE2 association
 RT_DEV float sum_importance(const float imp[8]) {
     return (imp[0] + imp[4]) + (imp[1] + imp[5]) + (imp[2] + imp[6]) + (imp[3] + imp[7]);
@@ -310,9 +396,8 @@ RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, co
     uint32_t i = 0;
     while ((i & kLeafBit) == 0) {
         const LightCWNode &n = sl.nodes[i];
-        float bmin[24], bmax[24], importance[8];
-        unpack_cw_bounds(n, bmin, bmax);
-        lnode_importance(n, bmin, bmax, P, importance);
+        float importance[8];
+        lnode_importance_q(n, P, importance);
         const float total_importance = sum_importance(importance);
         if (total_importance == 0.0f) {
             return; // no light can be sampled from here

@@ -451,6 +451,10 @@ struct MatCtx {
     uint32_t tri_index;
     uint32_t *tl_stack;
     float *tl_factors;
+    // carried between the phases of shade_surface_{a,l,b}
+    uint32_t rand_dim, rand_hash;
+    float term_rand_y, cone_width;
+    int iteration;
 };
 
 RT_FN void shade_node_diffuse(MatCtx &c) {
@@ -919,9 +923,13 @@ RT_FN void shade_node_principled(MatCtx &c) {
 }
 
 // One invocation of Ref::ShadeSurface.  `limits` = {direct, indirect} clamp limits (FLT_MAX when clamping is off).
-RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, const Hit &inter, const RayD &ray,
-                          uint32_t rand_seed, int iteration, const ShadeScene &sc, uint32_t *tl_stack,
-                          float *tl_factors, ShadeOut &out) {
+// ShadeSurface (ShadeRef.cpp:1173-1652) in three phases so that the kernel can keep the warps of a block in step between
+// them (RT_SHADE_SYNC):  a = miss / light hit / surface frame + mix resolution,  l = light sampling (NEE),
+// b = the material node + path continuation.  `c` carries everything from one phase to the next.
+// Phase a returns false when the ray is finished (out.col is final).
+RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &inter, const RayD &ray, uint32_t rand_seed,
+                            int iteration, const ShadeScene &sc, uint32_t *tl_stack, float *tl_factors, MatCtx &c,
+                            ShadeOut &out) {
     out.has_secondary = out.has_shadow = false;
     out.wrote_aov = false;
     out.base_color = v3{0.0f, 0.0f, 0.0f};
@@ -967,10 +975,10 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
             env_col.w *= k;
         }
         out.col = env_col;
-        return;
+        return false;
     }
 
-    Surface surf;
+    Surface &surf = c.surf; // the surface and the light sample are built in place in the context the node functions read
     surf.P = ro + inter.t * I;
 
     if (inter.obj < 0) { // analytic light hit: Evaluate_LightColor :1068-1172
@@ -1040,7 +1048,7 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
             lcol *= (limit0 / sum);
         }
         out.col = c4{lcol.x, lcol.y, lcol.z, 1.0f};
-        return;
+        return false;
     }
 
     const bool is_backfacing = (inter.prim < 0);
@@ -1067,7 +1075,7 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
     if (is_backfacing) {
         if (tm.back_mi == 0xffff) {
             out.col = c4{0.0f, 0.0f, 0.0f, 0.0f};
-            return;
+            return false;
         } else {
             mat = &sc.surf.materials[tm.back_mi & kMatIndexBits];
             surf.plane_N = -surf.plane_N;
@@ -1147,7 +1155,41 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
         surf.T = cross(surf.N, surf.B);
     }
 
-    LightSample ls;
+    c.ps = &ps;
+    c.ray = &ray;
+    c.sc = &sc;
+    c.inter = &inter;
+    c.mat = mat;
+    c.mi = mi;
+    c.vtx1 = &v1;
+    c.vtx2 = &v2_;
+    c.vtx3 = &v3_;
+    c.col = col;
+    c.I = I;
+    c.ro = ro;
+    c.mix_weight = mix_weight;
+    c.mix_rand = mix_rand;
+    c.ext_ior = ext_ior;
+    c.is_backfacing = is_backfacing;
+    c.diff_d = diff_d;
+    c.spec_d = spec_d;
+    c.refr_d = refr_d;
+    c.total_d = total_d;
+    c.tri_index = tri_index;
+    c.tl_stack = tl_stack;
+    c.tl_factors = tl_factors;
+    c.rand_dim = rand_dim;
+    c.rand_hash = rand_hash;
+    c.term_rand_y = mix_term_rand.y;
+    c.cone_width = cone_width;
+    c.iteration = iteration;
+    return true;
+}
+
+RT_DEV void shade_surface_l(MatCtx &c) {
+    const ShadeScene &sc = *c.sc;
+    const Surface &surf = c.surf;
+    LightSample &ls = c.ls;
     ls.col = ls.L = ls.lp = v3{0.0f, 0.0f, 0.0f};
     ls.area = 0.0f;
     ls.dist_mul = 1.0f;
@@ -1155,12 +1197,29 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
     ls.cast_shadow = false;
     ls.from_env = false;
     ls.ray_flags = 0;
-    if (sc.lights.nodes_count != 0 && mat->type != NODE_EMISSIVE) {
-        const float rand_pick_light = rand2d(rand_dim + kRandDimLightPick, rand_hash, iteration - 1, sc.rand_seq).x;
-        const v2 rand_light_uv = rand2d(rand_dim + kRandDimLight, rand_hash, iteration - 1, sc.rand_seq);
+    if (sc.lights.nodes_count != 0 && c.mat->type != NODE_EMISSIVE) {
+        const float rand_pick_light =
+            rand2d(c.rand_dim + kRandDimLightPick, c.rand_hash, c.iteration - 1, sc.rand_seq).x;
+        const v2 rand_light_uv = rand2d(c.rand_dim + kRandDimLight, c.rand_hash, c.iteration - 1, sc.rand_seq);
         sample_light_source(surf.P, surf.T, surf.B, surf.N, sc.lights, sc.geo, sc.surf, rand_pick_light, rand_light_uv,
                             ls);
     }
+}
+
+RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
+    const PassSettings &ps = *c.ps;
+    const RayD &ray = *c.ray;
+    const ShadeScene &sc = *c.sc;
+    const Hit &inter = *c.inter;
+    const Surface &surf = c.surf;
+    const LightSample &ls = c.ls;
+    const Material *mat = c.mat;
+    const uint32_t rand_dim = c.rand_dim, rand_hash = c.rand_hash;
+    const int iteration = c.iteration;
+    const float cone_width = c.cone_width, ext_ior = c.ext_ior, mix_weight = c.mix_weight, mix_rand = c.mix_rand;
+    const bool is_backfacing = c.is_backfacing;
+    const int diff_d = c.diff_d, total_d = c.total_d;
+    v3 col = c.col;
     const float N_dot_L = dot(surf.N, ls.L);
 
     const v3 base_color = mk3(mat->base_color);
@@ -1202,42 +1261,16 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
     const bool use_mis = (total_d < ps.max_total_depth);
 
     {
-        MatCtx c;
-        c.ps = &ps;
-        c.ray = &ray;
-        c.sc = &sc;
-        c.inter = &inter;
-        c.surf = surf;
-        c.ls = ls;
-        c.mat = mat;
-        c.mi = mi;
-        c.vtx1 = &v1;
-        c.vtx2 = &v2_;
-        c.vtx3 = &v3_;
         c.new_ray = &new_ray;
         c.sh_r = &sh_r;
-        c.col = col;
-        c.I = I;
-        c.ro = ro;
         c.base_color = base_color;
         c.tint_color = tint_color;
         c.N_dot_L = N_dot_L;
         c.roughness = roughness;
-        c.mix_weight = mix_weight;
-        c.mix_rand = mix_rand;
         c.regularize_alpha = regularize_alpha;
-        c.ext_ior = ext_ior;
         c.base_color_lum = base_color_lum;
         c.rand_bsdf = rand_bsdf;
         c.use_mis = use_mis;
-        c.is_backfacing = is_backfacing;
-        c.diff_d = diff_d;
-        c.spec_d = spec_d;
-        c.refr_d = refr_d;
-        c.total_d = total_d;
-        c.tri_index = tri_index;
-        c.tl_stack = tl_stack;
-        c.tl_factors = tl_factors;
         switch (mat->type) {
         case NODE_DIFFUSE: shade_node_diffuse(c); break;
         case NODE_GLOSSY: shade_node_glossy(c); break;
@@ -1253,7 +1286,7 @@ RT_DEV void shade_surface(const PassSettings &ps, float limit0, float limit1, co
 
     new_ray.c = new_ray.c * ray.c;
     const float lum_ = fmaxf(new_ray.c.x, fmaxf(new_ray.c.y, new_ray.c.z));
-    const float p = mix_term_rand.y;
+    const float p = c.term_rand_y;
     const float q = can_terminate_path ? fmaxf(0.05f, 1.0f - lum_) : 0.0f;
     if (p >= q && lum_ > 0.0f && new_ray.pdf > 0.0f) {
         new_ray.pdf = fminf(new_ray.pdf, 1e6f);
