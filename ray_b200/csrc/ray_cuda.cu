@@ -115,22 +115,26 @@ int upload_array(rc_ctx *ctx, DevArray &dst, const rc_array &src, uint32_t expec
     if (src.count != 0 && src.stride != expected_stride) {
         return fail(ctx, "rc_upload_scene: %s stride %u != %u", name, src.stride, expected_stride);
     }
-    if (dst.ptr) {
-        cudaFree(dst.ptr);
-        dst = DevArray{};
+    const size_t new_bytes = size_t(src.count) * expected_stride;
+    if (new_bytes != 0 && !src.ptr) {
+        return fail(ctx, "rc_upload_scene: %s has count %u but a null pointer", name, src.count);
+    }
+    // a re-upload of an array whose size did not change (the common case: animated transforms, edited materials)
+    // reuses the device allocation: cudaFree + cudaMalloc cost milliseconds and synchronise the device
+    if (!(dst.ptr && new_bytes != 0 && dst.bytes == new_bytes)) {
+        if (dst.ptr) {
+            cudaFree(dst.ptr);
+            dst = DevArray{};
+        }
+        CU_CHECK(ctx, cudaMalloc(&dst.ptr, new_bytes ? new_bytes : 256));
     }
     dst.count = src.count;
-    dst.bytes = size_t(src.count) * expected_stride;
-    if (dst.bytes == 0) {
-        // keep a valid non-null pointer so kernels can form (never dereferenced) addresses
-        CU_CHECK(ctx, cudaMalloc(&dst.ptr, 256));
+    dst.bytes = new_bytes;
+    if (new_bytes == 0) {
+        // a valid non-null pointer so kernels can form (never dereferenced) addresses
         CU_CHECK(ctx, cudaMemsetAsync(dst.ptr, 0, 256, ctx->stream));
         return 0;
     }
-    if (!src.ptr) {
-        return fail(ctx, "rc_upload_scene: %s has count %u but a null pointer", name, src.count);
-    }
-    CU_CHECK(ctx, cudaMalloc(&dst.ptr, dst.bytes));
     CU_CHECK(ctx, cudaMemcpyAsync(dst.ptr, src.ptr, dst.bytes, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
@@ -337,6 +341,14 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     }
 
     CU_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t), s));
+    if (do_sort) {
+        // k_shade emits sort keys + per-list histograms while it writes the secondary rays
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->sort.hist, 0, size_t(max_bounces + 2) * kSortBins * sizeof(uint32_t), s));
+        p.sort_grid = SortGrid{ctx->sort.root_min[0], ctx->sort.root_min[1], ctx->sort.root_min[2],
+                               ctx->sort.inv_cell[0], ctx->sort.inv_cell[1], ctx->sort.inv_cell[2]};
+        p.sort_keys = ctx->sort.keys;
+        p.sort_hist = ctx->sort.hist;
+    }
     record(ctx, EV_START);
 
     const int n_pix_tiles = ((p.rect_w + 7) / 8) * ((p.rect_h + 3) / 4);
@@ -374,9 +386,10 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     for (int bounce = 1; bounce <= max_bounces; ++bounce) {
         const int e = EV_BOUNCE0 + (bounce - 1) * kEventsPerBounce;
         if (do_sort) {
-            sort_rays(ctx->sort, p, ctx->rays[cur], ctx->rays[cur ^ 1], bounce, ctx->num_sms, s);
+            sort_rays(ctx->sort, p, ctx->rays[cur], ctx->rays[cur ^ 1], bounce, ctx->num_sms, /*have_hist*/ true,
+                      /*want_sorted_keys*/ false, s);
             cur ^= 1; // the reordered list now lives in the other buffer; the old one is free for this bounce's output
-            ctx->kernel_launches[KF_SORT] += 3;
+            ctx->kernel_launches[KF_SORT] += 2;
         }
         record(ctx, e + 0);
         if (have_geo) {
@@ -1105,7 +1118,8 @@ int rc_stage_sort_rays(rc_ctx *ctx, void *rays, int count, uint32_t *hashes_out)
         set_counter(ctx, CNT_RAYS + 1, uint32_t(count))) {
         return 1;
     }
-    sort_rays(ctx->sort, p, ctx->rays[0], ctx->rays[1], 1, ctx->num_sms, ctx->stream);
+    sort_rays(ctx->sort, p, ctx->rays[0], ctx->rays[1], 1, ctx->num_sms, /*have_hist*/ false,
+              /*want_sorted_keys*/ true, ctx->stream);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaGetLastError());
     if (download_rays_aos(ctx, ctx->rays[1], static_cast<RayAoS *>(rays), count)) {

@@ -58,6 +58,27 @@ enum : int {
 // persistent totals (uint64)
 enum : int { TOT_PRIMARY = 0, TOT_SECONDARY, TOT_SHADOW, TOT_NODES, TOT_LEAVES, TOT_SAMPLES, TOT_COUNT };
 
+// ---- sort key of the inter-bounce ray reordering (rt_sort.cuh) -----------------------------------------------------
+constexpr int kSortKeyBits = 15;
+constexpr int kSortBins = 1 << kSortKeyBits;
+
+struct SortGrid {
+    float min_x, min_y, min_z, inv_x, inv_y, inv_z;
+};
+
+RT_DEV uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+}
+
+RT_DEV uint32_t ray_sort_key(float4 o, float4 d, const SortGrid &g) {
+    const int cx = min(max(int((o.x - g.min_x) * g.inv_x), 0), 15);
+    const int cy = min(max(int((o.y - g.min_y) * g.inv_y), 0), 15);
+    const int cz = min(max(int((o.z - g.min_z) * g.inv_z), 0), 15);
+    const uint32_t morton = spread4(uint32_t(cx)) | (spread4(uint32_t(cy)) << 1) | (spread4(uint32_t(cz)) << 2);
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    return (oct << 12) | morton;
+}
+
 struct CamParams { // derived once per pass on the host (tanf/atanf come from the host libm like the reference's)
     v3 origin, fwd, side, up;
     float shift_x, shift_y;
@@ -85,6 +106,11 @@ struct KParams {
     int rect_x, rect_y, rect_w, rect_h;
     int iteration;
     uint32_t rand_seed;
+    // ray reordering (rt_sort.cuh): when sort_hist != nullptr, k_shade also emits the sort key of every secondary ray
+    // it stores and counts it in the histogram of the list it appends to (sort_hist + list * kSortBins)
+    SortGrid sort_grid;
+    uint32_t *sort_keys;
+    uint32_t *sort_hist;
 };
 
 RT_DEV RayD load_ray(const RayBuf &b, uint32_t i) {
@@ -476,6 +502,13 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS)
         const uint32_t s_slot = warp_append(&p.counters[CNT_RAYS + bounce + 1], out.has_secondary);
         if (out.has_secondary) {
             store_ray(out_rays, s_slot, out.new_ray);
+            if (p.sort_hist) {
+                const RayD &nr = out.new_ray;
+                const uint32_t key = ray_sort_key(make_float4(nr.o.x, nr.o.y, nr.o.z, 0.0f),
+                                                  make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f), p.sort_grid);
+                p.sort_keys[s_slot] = key;
+                atomicAdd(&p.sort_hist[size_t(bounce + 1) * kSortBins + key], 1u);
+            }
             // initial hit record for the next trace (RendererCPU.h:532-535: `intersections[i] = {}`)
         }
         const uint32_t h_slot = warp_append(&p.counters[CNT_SHADOW + bounce], out.has_shadow);

@@ -1216,9 +1216,8 @@ RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
     const Material *mat = c.mat;
     const uint32_t rand_dim = c.rand_dim, rand_hash = c.rand_hash;
     const int iteration = c.iteration;
-    const float cone_width = c.cone_width, ext_ior = c.ext_ior, mix_weight = c.mix_weight, mix_rand = c.mix_rand;
-    const bool is_backfacing = c.is_backfacing;
-    const int diff_d = c.diff_d, total_d = c.total_d;
+    const float cone_width = c.cone_width;
+    const int total_d = c.total_d;
     v3 col = c.col;
     const float N_dot_L = dot(surf.N, ls.L);
 

@@ -16,13 +16,10 @@
 
 namespace rt {
 
-constexpr int kSortKeyBits = 15;
-constexpr int kSortBins = 1 << kSortKeyBits;
-
 struct SortBufs {
     uint32_t *keys = nullptr;        // key per input ray
     uint32_t *keys_sorted = nullptr; // key per output ray (diagnostics / stage API)
-    uint32_t *hist = nullptr;        // kSortBins
+    uint32_t *hist = nullptr;        // kMaxBounces x kSortBins: one histogram per ray list, zeroed once per sample
     float root_min[3] = {0, 0, 0};
     float inv_cell[3] = {1, 1, 1};
 };
@@ -31,7 +28,7 @@ inline int alloc_sort_bufs(SortBufs &s, size_t n) {
     cudaFree(s.keys);
     cudaFree(s.keys_sorted);
     s.keys = s.keys_sorted = nullptr;
-    if (!s.hist && cudaMalloc(&s.hist, kSortBins * sizeof(uint32_t)) != cudaSuccess) {
+    if (!s.hist && cudaMalloc(&s.hist, size_t(kMaxBounces) * kSortBins * sizeof(uint32_t)) != cudaSuccess) {
         return 1;
     }
     if (n == 0) {
@@ -59,23 +56,6 @@ inline void set_sort_bounds(SortBufs &s, const float bmin[3], const float bmax[3
     }
 }
 
-struct SortGrid {
-    float min_x, min_y, min_z, inv_x, inv_y, inv_z;
-};
-
-RT_DEV uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
-    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
-}
-
-RT_DEV uint32_t ray_sort_key(float4 o, float4 d, const SortGrid &g) {
-    const int cx = min(max(int((o.x - g.min_x) * g.inv_x), 0), 15);
-    const int cy = min(max(int((o.y - g.min_y) * g.inv_y), 0), 15);
-    const int cz = min(max(int((o.z - g.min_z) * g.inv_z), 0), 15);
-    const uint32_t morton = spread4(uint32_t(cx)) | (spread4(uint32_t(cy)) << 1) | (spread4(uint32_t(cz)) << 2);
-    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-    return (oct << 12) | morton;
-}
-
 __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *counters, int bounce, RayBuf rays, SortGrid g,
                                                    uint32_t *keys, uint32_t *hist) {
     const uint32_t count = counters[CNT_RAYS + bounce];
@@ -86,48 +66,50 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *counters, int
     }
 }
 
-// exclusive scan of kSortBins counters by one 1024-thread block (32 bins per thread)
+// exclusive scan of kSortBins counters by one 1024-thread block.  Warp w owns bins [1024 w, 1024 (w+1)) as 32 rows of
+// 32: every load and store is a coalesced 128-byte row, the scan inside a row is a shuffle scan.
 __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *hist) {
+    static_assert(kSortBins == 32 * 1024, "one warp per 1024 bins");
     __shared__ uint32_t warp_sums[32];
-    constexpr int per_thread = kSortBins / 1024;
-    const int tid = threadIdx.x;
-    uint32_t local[per_thread];
-    uint32_t sum = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *row0 = hist + warp * 1024 + lane;
+    uint32_t excl[32];
+    uint32_t running = 0;
 #pragma unroll
-    for (int j = 0; j < per_thread; ++j) {
-        local[j] = hist[tid * per_thread + j];
-        sum += local[j];
-    }
-    // inclusive scan of `sum` across the block
-    uint32_t incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-        if ((tid & 31) >= off) {
-            incl += v;
-        }
-    }
-    if ((tid & 31) == 31) {
-        warp_sums[tid >> 5] = incl;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        uint32_t w = warp_sums[tid];
+    for (int r = 0; r < 32; ++r) {
+        const uint32_t v = row0[r * 32];
+        uint32_t incl = v;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, w, off);
-            if (tid >= off) {
-                w += v;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) {
+                incl += u;
             }
         }
-        warp_sums[tid] = w;
+        excl[r] = running + incl - v;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        warp_sums[warp] = running;
     }
     __syncthreads();
-    uint32_t base = incl - sum + ((tid >> 5) ? warp_sums[(tid >> 5) - 1] : 0u);
+    if (warp == 0) {
+        const uint32_t t = warp_sums[lane];
+        uint32_t w = t;
 #pragma unroll
-    for (int j = 0; j < per_thread; ++j) {
-        hist[tid * per_thread + j] = base;
-        base += local[j];
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) {
+                w += u;
+            }
+        }
+        warp_sums[lane] = w - t;
+    }
+    __syncthreads();
+    const uint32_t base = warp_sums[warp];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        row0[r * 32] = base + excl[r];
     }
 }
 
@@ -142,18 +124,26 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t *counters, 
         dst.c_pdf[slot] = src.c_pdf[i];
         dst.ior[slot] = src.ior[i];
         dst.xy_depth[slot] = src.xy_depth[i];
-        keys_sorted[slot] = key;
+        if (keys_sorted) {
+            keys_sorted[slot] = key;
+        }
     }
 }
 
 // Reorders list `bounce` from `src` into `dst` (caller swaps its notion of the current buffer).
+// have_hist: keys and the histogram of this list were already produced by the kernel that wrote the list (k_shade, see
+// KParams::sort_hist), so the 32 B/ray key pass is skipped; otherwise (stage API) they are built here.
 inline void sort_rays(SortBufs &s, const KParams &p, const RayBuf &src, const RayBuf &dst, int bounce, int num_sms,
-                      cudaStream_t stream) {
-    SortGrid g{s.root_min[0], s.root_min[1], s.root_min[2], s.inv_cell[0], s.inv_cell[1], s.inv_cell[2]};
-    cudaMemsetAsync(s.hist, 0, kSortBins * sizeof(uint32_t), stream);
-    k_sort_hist<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, g, s.keys, s.hist);
-    k_sort_scan<<<1, 1024, 0, stream>>>(s.hist);
-    k_sort_scatter<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, dst, s.keys, s.hist, s.keys_sorted);
+                      bool have_hist, bool want_sorted_keys, cudaStream_t stream) {
+    uint32_t *hist = s.hist + size_t(bounce) * kSortBins;
+    if (!have_hist) {
+        SortGrid g{s.root_min[0], s.root_min[1], s.root_min[2], s.inv_cell[0], s.inv_cell[1], s.inv_cell[2]};
+        cudaMemsetAsync(hist, 0, kSortBins * sizeof(uint32_t), stream);
+        k_sort_hist<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, g, s.keys, hist);
+    }
+    k_sort_scan<<<1, 1024, 0, stream>>>(hist);
+    k_sort_scatter<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, dst, s.keys, hist,
+                                                    want_sorted_keys ? s.keys_sorted : nullptr);
 }
 
 } // namespace rt
