@@ -16,9 +16,17 @@
 #include "rt_types.h"
 
 #define RT_DEV __device__ __forceinline__
-// Heavy leaf functions are real calls: the shade kernel was 460 KB of SASS when everything was inlined and stalled on
-// instruction fetch (ncu: no_instruction 1.6-4.0 stalls per issue).  Inlining never changes results here (-fmad=false).
-#define RT_FN __device__ __noinline__
+// RT_FN marks the heavy leaf functions (BSDF nodes, light sampling, normalize, ...).  History, all on hall-250k:
+//   everything inlined, 128-thread blocks:   k_shade = 460 KB of SASS, I-cache hit 65 %, no_instruction 4-5 stalls/issue
+//   RT_FN = noinline (real calls):           177 KB, -25 % time, but every context struct lives in local memory
+//                                            (2 GB of DRAM writes per launch)
+//   inlined again + block-synchronised warps (RT_SHADE_SYNC, rt_kernels.cuh): the warps of a 512-thread block walk
+//   the straight-line code together and share instruction-cache lines -> 118 -> 54 ms per 16 samples.
+// Inlining never changes results here (-fmad=false, no contraction across calls).  -DRT_FN="__device__ __noinline__"
+// restores the call-based build for A/B measurements.
+#ifndef RT_FN
+#define RT_FN __device__ __forceinline__
+#endif
 
 namespace rt {
 
