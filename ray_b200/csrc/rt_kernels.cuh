@@ -59,24 +59,39 @@ enum : int {
 enum : int { TOT_PRIMARY = 0, TOT_SECONDARY, TOT_SHADOW, TOT_NODES, TOT_LEAVES, TOT_SAMPLES, TOT_COUNT };
 
 // ---- sort key of the inter-bounce ray reordering (rt_sort.cuh) -----------------------------------------------------
-constexpr int kSortKeyBits = 15;
+// key = direction octant (3 bits, major) | Morton code of the origin in a (2^kSortCellBits)^3 grid over the scene bounds
+#ifndef RT_SORT_CELL_BITS
+#define RT_SORT_CELL_BITS 4
+#endif
+constexpr int kSortCellBits = RT_SORT_CELL_BITS;
+constexpr int kSortKeyBits = 3 + 3 * kSortCellBits;
 constexpr int kSortBins = 1 << kSortKeyBits;
 
 struct SortGrid {
     float min_x, min_y, min_z, inv_x, inv_y, inv_z;
 };
 
-RT_DEV uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
-    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+RT_DEV uint32_t spread3(uint32_t v) { // bit i -> bit 3 i
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < kSortCellBits; ++i) {
+        r |= ((v >> i) & 1u) << (3 * i);
+    }
+    return r;
 }
 
 RT_DEV uint32_t ray_sort_key(float4 o, float4 d, const SortGrid &g) {
-    const int cx = min(max(int((o.x - g.min_x) * g.inv_x), 0), 15);
-    const int cy = min(max(int((o.y - g.min_y) * g.inv_y), 0), 15);
-    const int cz = min(max(int((o.z - g.min_z) * g.inv_z), 0), 15);
-    const uint32_t morton = spread4(uint32_t(cx)) | (spread4(uint32_t(cy)) << 1) | (spread4(uint32_t(cz)) << 2);
+    constexpr int hi = (1 << kSortCellBits) - 1;
+    const int cx = min(max(int((o.x - g.min_x) * g.inv_x), 0), hi);
+    const int cy = min(max(int((o.y - g.min_y) * g.inv_y), 0), hi);
+    const int cz = min(max(int((o.z - g.min_z) * g.inv_z), 0), hi);
+    const uint32_t morton = spread3(uint32_t(cx)) | (spread3(uint32_t(cy)) << 1) | (spread3(uint32_t(cz)) << 2);
     const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-    return (oct << 12) | morton;
+#if defined(RT_SORT_ORIGIN_MAJOR) && RT_SORT_ORIGIN_MAJOR
+    return (morton << 3) | oct;
+#else
+    return (oct << (3 * kSortCellBits)) | morton;
+#endif
 }
 
 struct CamParams { // derived once per pass on the host (tanf/atanf come from the host libm like the reference's)

@@ -52,7 +52,7 @@ inline void set_sort_bounds(SortBufs &s, const float bmin[3], const float bmax[3
     for (int i = 0; i < 3; ++i) {
         s.root_min[i] = bmin[i];
         const float ext = bmax[i] - bmin[i];
-        s.inv_cell[i] = (ext > 0.0f) ? 16.0f / ext : 0.0f;
+        s.inv_cell[i] = (ext > 0.0f) ? float(1 << kSortCellBits) / ext : 0.0f;
     }
 }
 
@@ -66,50 +66,59 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *counters, int
     }
 }
 
-// exclusive scan of kSortBins counters by one 1024-thread block.  Warp w owns bins [1024 w, 1024 (w+1)) as 32 rows of
-// 32: every load and store is a coalesced 128-byte row, the scan inside a row is a shuffle scan.
+// exclusive scan of kSortBins counters by one 1024-thread block, 32768 bins per round.  Warp w owns bins
+// [1024 w, 1024 (w+1)) of the round as 32 rows of 32: every load and store is a coalesced 128-byte row, the scan inside
+// a row is a shuffle scan.
 __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *hist) {
-    static_assert(kSortBins == 32 * 1024, "one warp per 1024 bins");
-    __shared__ uint32_t warp_sums[32];
+    static_assert(kSortBins % (32 * 1024) == 0, "whole rounds");
+    __shared__ uint32_t warp_sums[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *row0 = hist + warp * 1024 + lane;
-    uint32_t excl[32];
-    uint32_t running = 0;
+    uint32_t carry = 0;
+    for (int round = 0; round < kSortBins / (32 * 1024); ++round) {
+        uint32_t *row0 = hist + round * (32 * 1024) + warp * 1024 + lane;
+        uint32_t excl[32];
+        uint32_t running = 0;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const uint32_t v = row0[r * 32];
-        uint32_t incl = v;
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t v = row0[r * 32];
+            uint32_t incl = v;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) {
-                incl += u;
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) {
+                    incl += u;
+                }
+            }
+            excl[r] = running + incl - v;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            warp_sums[warp] = running;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t t = warp_sums[lane];
+            uint32_t w = t;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off) {
+                    w += u;
+                }
+            }
+            warp_sums[lane] = w - t;
+            if (lane == 31) {
+                warp_sums[32] = w; // total of this round
             }
         }
-        excl[r] = running + incl - v;
-        running += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) {
-        warp_sums[warp] = running;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t t = warp_sums[lane];
-        uint32_t w = t;
+        __syncthreads();
+        const uint32_t base = carry + warp_sums[warp];
+        carry += warp_sums[32];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, w, off);
-            if (lane >= off) {
-                w += u;
-            }
+        for (int r = 0; r < 32; ++r) {
+            row0[r * 32] = base + excl[r];
         }
-        warp_sums[lane] = w - t;
-    }
-    __syncthreads();
-    const uint32_t base = warp_sums[warp];
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        row0[r * 32] = base + excl[r];
+        __syncthreads();
     }
 }
 
