@@ -41,6 +41,21 @@ typedef struct rc_array {
     uint32_t stride;
 } rc_array;
 
+/* One texture of the scene's texture storages (reference internal/TextureStorageCPU.h, SceneCPU.h:65-76), handed over
+ * DECODED: row-major 8-bit texels, `channels` per texel, one pointer per mip level.  `handle` is what material_t::textures[]
+ * and light_t::tri.tex_index carry without the flag bits 24..27: (storage << 28) | index (Core.h:159-161,
+ * SceneCPU.cpp:191-204).  The texel a lookup returns is the one TexStorageBase::Fetch(index, x, y, lod) returns
+ * (x %= w, y %= h; channels missing in the storage repeat the last stored one; value = byte / 255.0f), so the binding on
+ * the reference side either walks Fetch() or hands over its pixel arrays.  Levels the storage does not have alias the
+ * last real one exactly as TexStorage*::Allocate fills res[]/lod_offsets[] (TextureStorageCPU.cpp:234-250). */
+#define RC_TEX_MIP_LEVELS 12 /* NUM_MIP_LEVELS, Constants.inl:91 */
+typedef struct rc_texture {
+    uint32_t handle;
+    uint32_t channels; /* 1..4 */
+    uint16_t res[RC_TEX_MIP_LEVELS][2];
+    const uint8_t *pixels[RC_TEX_MIP_LEVELS];
+} rc_texture;
+
 /* View of a finalized wide-BVH Cpu::Scene (reference internal/SceneCPU.h:50-98).  Layouts are the reference's
  * (internal/Core.h); strides are checked against them. */
 typedef struct rc_scene_view {
@@ -66,6 +81,11 @@ typedef struct rc_scene_view {
     float sky_map_spread_angle; /* must be 0 */
     /* Cpu::Scene::GetBounds (ray-sort grid) */
     float bounds_min[3], bounds_max[3];
+    /* textures referenced by materials / triangle lights (NULL / 0 for an untextured scene).  YCoCg-coded textures
+     * (TEX_YCOCG_BIT, only produced with texture compression on) are rejected. */
+    const rc_texture *textures;
+    uint32_t texture_count;
+    uint32_t _pad0;
 } rc_scene_view;
 
 /* camera_t (reference Types.h:102-115) + pass_settings_t (Types.h:92-100), flattened to 32-bit fields. */

@@ -85,6 +85,20 @@ typedef struct rs_principled_mat_desc {
     uint32_t importance_sample; /* bool */
 } rs_principled_mat_desc;
 
+/* tex_desc_t (SceneBase.h:177-192), uncompressed formats.  The returned handle is the reference's TextureHandle::_index:
+ * (storage << 28) | flag bits 24..27 | index (SceneCPU.cpp:191-204). */
+enum { RS_TEX_RGBA8888 = 1, RS_TEX_RGB888 = 2, RS_TEX_RG88 = 3, RS_TEX_R8 = 4 }; /* eTextureFormat, SceneBase.h:145 */
+typedef struct rs_tex_desc {
+    uint32_t format;      /* RS_TEX_* */
+    uint32_t convention;  /* eTextureConvention: 0 = OGL, 1 = DX (inverts y of normal maps) */
+    const uint8_t *data;  /* w * h texels, row-major */
+    int32_t w, h;
+    uint32_t is_srgb;          /* bool, default 1 */
+    uint32_t is_normalmap;     /* bool */
+    uint32_t generate_mipmaps; /* bool (the uncompressed storages ignore it, TextureStorageCPU.cpp:232) */
+    uint32_t reconstruct_z;    /* bool */
+} rs_tex_desc;
+
 typedef struct rs_mat_group_desc {
     uint32_t front_mat;
     uint32_t back_mat;

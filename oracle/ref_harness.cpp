@@ -20,6 +20,7 @@
 #include <functional>
 #include <memory>
 #include <thread>
+#include <list>
 #include <vector>
 
 #include "Ray.h"
@@ -106,9 +107,49 @@ class OracleScene final : public Cpu::Scene {
         v.env_light_index = env_.light_index;
         v.sky_map_spread_angle = env_.sky_map_spread_angle;
         GetBounds(v.bounds_min, v.bounds_max);
+        export_textures(v);
     }
 
     const camera_t &cam() const { return cams_[current_cam_._index]; }
+
+    // Textures cross the C-ABI decoded (include/ray_cuda.h rc_texture): walk the storage's own Fetch(), which applies the
+    // swizzle / block decode and the channel expansion, and turn byte / 255.0f back into the byte.
+    void add_texture_handle(uint32_t h) { tex_handles_.push_back(h); }
+    void export_textures(rc_scene_view &v) const {
+        tex_pixels_.clear();
+        tex_views_.clear();
+        for (const uint32_t h : tex_handles_) {
+            const Cpu::TexStorageBase *st = tex_storages_[h >> 28];
+            const int index = int(h & 0x00ffffff);
+            rc_texture t = {};
+            t.handle = h & 0xf0ffffffu;
+            t.channels = 4;
+            for (int lod = 0; lod < NUM_MIP_LEVELS; ++lod) {
+                int res[2];
+                st->GetIRes(index, lod, res);
+                t.res[lod][0] = uint16_t(res[0]);
+                t.res[lod][1] = uint16_t(res[1]);
+                if (lod > 0 && res[0] == t.res[lod - 1][0] && res[1] == t.res[lod - 1][1]) {
+                    t.pixels[lod] = t.pixels[lod - 1]; // level absent: aliases the previous one (Allocate, :244-249)
+                    continue;
+                }
+                tex_pixels_.emplace_back(size_t(res[0]) * res[1] * 4);
+                uint8_t *dst = tex_pixels_.back().data();
+                for (int y = 0; y < res[1]; ++y) {
+                    for (int x = 0; x < res[0]; ++x) {
+                        const color_rgba_t c = st->Fetch(index, x, y, lod);
+                        for (int k = 0; k < 4; ++k) {
+                            dst[(size_t(y) * res[0] + x) * 4 + k] = uint8_t(lrintf(c.v[k] * 255.0f));
+                        }
+                    }
+                }
+                t.pixels[lod] = dst;
+            }
+            tex_views_.push_back(t);
+        }
+        v.textures = tex_views_.empty() ? nullptr : tex_views_.data();
+        v.texture_count = uint32_t(tex_views_.size());
+    }
 
     // scene_data_t exactly as Cpu::Renderer<P>::RenderScene assembles it
     scene_data_t make_scene_data(const cache_grid_params_t &cache_grid) const {
@@ -139,6 +180,13 @@ class OracleScene final : public Cpu::Scene {
     }
 
     const Cpu::TexStorageBase *const *textures() const { return tex_storages_; }
+
+  private:
+    std::vector<uint32_t> tex_handles_;
+    mutable std::list<std::vector<uint8_t>> tex_pixels_;
+    mutable std::vector<rc_texture> tex_views_;
+
+  public:
     uint32_t tlas_root() const { return tlas_root_; }
     uint32_t counts(int which) const {
         switch (which) {
@@ -230,6 +278,26 @@ int ro_cpu_features(void) {
 
 ro_scene *ro_scene_create(int use_wide_bvh) { return reinterpret_cast<ro_scene *>(new OracleScene(use_wide_bvh != 0)); }
 void ro_scene_destroy(ro_scene *s) { delete reinterpret_cast<OracleScene *>(s); }
+
+uint32_t ro_add_texture(ro_scene *s, const rs_tex_desc *d) {
+    tex_desc_t t;
+    t.format = eTextureFormat(d->format);
+    t.convention = eTextureConvention(d->convention);
+    const int channels = TexFormatChannelCount[d->format];
+    t.data = Span<const uint8_t>{d->data, size_t(d->w) * d->h * channels};
+    t.w = d->w;
+    t.h = d->h;
+    t.is_srgb = d->is_srgb != 0;
+    t.is_normalmap = d->is_normalmap != 0;
+    t.generate_mipmaps = d->generate_mipmaps != 0;
+    t.reconstruct_z = d->reconstruct_z != 0;
+    t.force_no_compression = true;
+    const TextureHandle h = reinterpret_cast<OracleScene *>(s)->AddTexture(t);
+    if (h._index != 0xffffffffu) {
+        reinterpret_cast<OracleScene *>(s)->add_texture_handle(h._index);
+    }
+    return h._index;
+}
 
 uint32_t ro_add_material_node(ro_scene *s, const rs_shading_node_desc *d) {
     shading_node_desc_t m;

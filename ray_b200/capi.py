@@ -56,6 +56,14 @@ class rs_principled_mat_desc(C.Structure):
         return d
 
 
+RS_TEX_RGBA8888, RS_TEX_RGB888, RS_TEX_RG88, RS_TEX_R8 = 1, 2, 3, 4
+
+
+class rs_tex_desc(C.Structure):
+    _fields_ = [("format", u32), ("convention", u32), ("data", C.c_void_p), ("w", i32), ("h", i32), ("is_srgb", u32),
+                ("is_normalmap", u32), ("generate_mipmaps", u32), ("reconstruct_z", u32)]
+
+
 class rs_mat_group_desc(C.Structure):
     _fields_ = [("front_mat", u32), ("back_mat", u32), ("vtx_start", u64), ("vtx_count", u64)]
 
@@ -151,6 +159,14 @@ class rc_array(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("count", u32), ("stride", u32)]
 
 
+RC_TEX_MIP_LEVELS = 12
+
+
+class rc_texture(C.Structure):
+    _fields_ = [("handle", u32), ("channels", u32), ("res", (C.c_uint16 * 2) * RC_TEX_MIP_LEVELS),
+                ("pixels", C.c_void_p * RC_TEX_MIP_LEVELS)]
+
+
 class rc_scene_view(C.Structure):
     _fields_ = [("wnodes", rc_array), ("mtris", rc_array), ("tri_indices", rc_array), ("tri_materials", rc_array),
                 ("materials", rc_array), ("mesh_instances", rc_array), ("vertices", rc_array),
@@ -158,7 +174,7 @@ class rc_scene_view(C.Structure):
                 ("tlas_root", u32), ("visible_lights_count", u32), ("blocker_lights_count", u32),
                 ("env_col", f32 * 3), ("env_map", u32), ("back_col", f32 * 3), ("back_map", u32),
                 ("env_light_index", u32), ("sky_map_spread_angle", f32), ("bounds_min", f32 * 3),
-                ("bounds_max", f32 * 3)]
+                ("bounds_max", f32 * 3), ("textures", C.POINTER(rc_texture)), ("texture_count", u32), ("_pad0", u32)]
 
 
 class rc_camera(C.Structure):
@@ -199,3 +215,17 @@ def _apply(struct, kw):
                 cur[i] = x
         else:
             setattr(struct, k, v)
+
+
+def make_tex_desc(pixels, is_srgb=True, is_normalmap=False, generate_mipmaps=False, reconstruct_z=False, convention=0):
+    """rs_tex_desc over a (h, w, c) or (h, w) uint8 array; returns (desc, keep-alive array)."""
+    import numpy as np
+    a = np.ascontiguousarray(pixels, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, c = a.shape
+    fmt = {4: RS_TEX_RGBA8888, 3: RS_TEX_RGB888, 2: RS_TEX_RG88, 1: RS_TEX_R8}[c]
+    d = rs_tex_desc(fmt, convention, a.ctypes.data, w, h, 1 if is_srgb else 0, 1 if is_normalmap else 0,
+                    1 if generate_mipmaps else 0, 1 if reconstruct_z else 0)
+    d._keep = a
+    return d, a

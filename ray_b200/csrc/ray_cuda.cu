@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -60,6 +61,8 @@ struct rc_ctx {
 
     DevArray wnodes, mtris, tri_indices, tri_materials, materials, mesh_instances, vertices, vtx_indices, lights,
         light_cwnodes;
+    DevArray tex_descs, tex_texels;
+    float *d_srgb_lut = nullptr;
     bool have_scene = false;
     rc_scene_view scene_info{};
     uint32_t li_count = 0;
@@ -215,6 +218,9 @@ int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     p.sc.surf.vertices = static_cast<const Vertex *>(ctx->vertices.ptr);
     p.sc.surf.vtx_indices = static_cast<const uint32_t *>(ctx->vtx_indices.ptr);
     p.sc.surf.materials = static_cast<const Material *>(ctx->materials.ptr);
+    p.sc.tex.descs = ctx->tex_descs.count ? static_cast<const TexDesc *>(ctx->tex_descs.ptr) : nullptr;
+    p.sc.tex.texels = static_cast<const uint32_t *>(ctx->tex_texels.ptr);
+    p.sc.tex.srgb_lut = ctx->d_srgb_lut;
     p.sc.lights.lights = static_cast<const Light *>(ctx->lights.ptr);
     p.sc.lights.nodes = static_cast<const LightCWNode *>(ctx->light_cwnodes.ptr);
     p.sc.lights.nodes_count = ctx->light_cwnodes.count;
@@ -599,6 +605,18 @@ int rc_create(int device, rc_ctx **out_ctx) {
     }
     cudaMemset(ctx->d_counters, 0, CNT_TOTAL * sizeof(uint32_t));
     cudaMemset(ctx->d_totals, 0, TOT_COUNT * sizeof(unsigned long long));
+    { // srgb_to_linear (CoreRef.h:208-220) of the 256 values a texel channel can hold, with the HOST powf like the reference
+        float lut[256];
+        for (int i = 0; i < 256; ++i) {
+            const float c = float(i) / 255.0f;
+            lut[i] = (c > 0.04045f) ? powf((c + 0.055f) / 1.055f, 2.4f) : (c / 12.92f);
+        }
+        if (cudaMalloc(&ctx->d_srgb_lut, sizeof(lut)) != cudaSuccess ||
+            cudaMemcpy(ctx->d_srgb_lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess) {
+            rc_destroy(ctx);
+            return 6;
+        }
+    }
     // traversal stacks live in local memory: give L1 the whole carve-out
     cudaFuncSetAttribute(k_trace_closest<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -644,8 +662,10 @@ void rc_destroy(rc_ctx *ctx) {
     cudaFree(ctx->d_totals);
     cudaFree(ctx->d_pmj);
     cudaFree(ctx->d_filter_table);
+    cudaFree(ctx->d_srgb_lut);
     for (DevArray *a : {&ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
-                        &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes}) {
+                        &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
+                        &ctx->tex_descs, &ctx->tex_texels}) {
         cudaFree(a->ptr);
     }
     if (ctx->stream) {
@@ -772,30 +792,119 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
     if (sv->sky_map_spread_angle != 0.0f) {
         return fail(ctx, "rc_upload_scene: procedural sky is not supported by the CUDA backend");
     }
-    // textures are out of scope: reject instead of silently rendering something else
-    if (sv->materials.ptr && sv->materials.stride == sizeof(Material)) {
+    // ---- textures: decoded RGBA8 pool + descriptor table; handles in the device copies of the materials and triangle
+    // lights become flags | dense id (rt_tex.cuh) ----
+    std::vector<Material> mats;
+    std::vector<Light> lts;
+    if (sv->materials.count != 0) {
+        if (sv->materials.stride != sizeof(Material) || !sv->materials.ptr) {
+            return fail(ctx, "rc_upload_scene: materials stride %u != %zu", sv->materials.stride, sizeof(Material));
+        }
         const Material *m = static_cast<const Material *>(sv->materials.ptr);
-        // NOTE: callers pass `count` = number of live, contiguous slots (SparseStorage::size() when nothing was
-        // removed); slots past that are uninitialised in the reference's storage and must not be handed over.
-        for (uint32_t i = 0; i < sv->materials.count; ++i) {
-            if (m[i].type > NODE_PRINCIPLED) {
+        mats.assign(m, m + sv->materials.count);
+    }
+    if (sv->lights.count != 0) {
+        if (sv->lights.stride != sizeof(Light) || !sv->lights.ptr) {
+            return fail(ctx, "rc_upload_scene: lights stride %u != %zu", sv->lights.stride, sizeof(Light));
+        }
+        const Light *l = static_cast<const Light *>(sv->lights.ptr);
+        lts.assign(l, l + sv->lights.count);
+    }
+    std::vector<TexDesc> descs;
+    std::vector<uint32_t> texels;
+    std::map<uint32_t, uint32_t> dense; // (storage << 28 | index) -> id
+    if (sv->texture_count != 0 && !sv->textures) {
+        return fail(ctx, "rc_upload_scene: texture_count %u but a null textures pointer", sv->texture_count);
+    }
+    for (uint32_t ti = 0; ti < sv->texture_count; ++ti) {
+        const rc_texture &t = sv->textures[ti];
+        if (t.channels < 1 || t.channels > 4) {
+            return fail(ctx, "rc_upload_scene: texture %u has %u channels", ti, t.channels);
+        }
+        TexDesc d{};
+        for (int lod = 0; lod < RC_TEX_MIP_LEVELS; ++lod) {
+            const int w = t.res[lod][0], h = t.res[lod][1];
+            if (w <= 0 || h <= 0 || !t.pixels[lod]) {
+                return fail(ctx, "rc_upload_scene: texture %u level %d is empty (absent levels must alias the last real one)",
+                            ti, lod);
+            }
+            d.w[lod] = uint16_t(w);
+            d.h[lod] = uint16_t(h);
+            int alias = -1;
+            for (int k = 0; k < lod; ++k) {
+                if (t.pixels[k] == t.pixels[lod] && t.res[k][0] == w && t.res[k][1] == h) {
+                    alias = k;
+                    break;
+                }
+            }
+            if (alias >= 0) {
+                d.offset[lod] = d.offset[alias];
                 continue;
             }
-            // only the slots ShadeSurface reads for this node type are meaningful: AddMaterial zero-initialises
-            // material_t and leaves the others at 0 (SceneCPU.cpp:208-247); Mix keeps child ids in slots 3/4
-            const int n_slots = (m[i].type == NODE_PRINCIPLED) ? 5 : 3;
-            for (int t = 0; t < n_slots; ++t) {
-                if (m[i].type == NODE_MIX && t != kTexBase) {
-                    continue;
+            if (texels.size() + size_t(w) * h > 0xffffffffull) {
+                return fail(ctx, "rc_upload_scene: more than 2^32 texels");
+            }
+            d.offset[lod] = uint32_t(texels.size());
+            const uint8_t *src = t.pixels[lod];
+            const uint32_t n = t.channels;
+            for (size_t i = 0; i < size_t(w) * h; ++i) {
+                uint32_t c[4];
+                for (uint32_t k = 0; k < 4; ++k) {
+                    c[k] = src[i * n + (k < n ? k : n - 1)]; // TexStorage*::Fetch: missing channels repeat the last one
                 }
-                if (m[i].textures[t] != 0xffffffffu) {
-                    return fail(ctx, "rc_upload_scene: material %u uses texture slot %d; textures are not supported "
-                                     "by the CUDA backend",
-                                i, t);
-                }
+                texels.push_back(c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24));
+            }
+        }
+        dense[t.handle & 0xf0ffffffu] = uint32_t(descs.size());
+        descs.push_back(d);
+    }
+    auto patch = [&](uint32_t &h, const char *what, uint32_t owner, int slot) -> int {
+        if (h == 0xffffffffu) {
+            return 0;
+        }
+        if (h & kTexYCoCgBit) {
+            return fail(ctx, "rc_upload_scene: %s %u slot %d is a YCoCg-coded texture (texture compression); not supported",
+                        what, owner, slot);
+        }
+        const auto it = dense.find(h & 0xf0ffffffu);
+        if (it == dense.end()) {
+            return fail(ctx, "rc_upload_scene: %s %u slot %d references texture 0x%08x which is not in rc_scene_view::textures",
+                        what, owner, slot, h);
+        }
+        h = (h & 0x0f000000u) | it->second;
+        return 0;
+    };
+    for (uint32_t i = 0; i < mats.size(); ++i) {
+        Material &m = mats[i];
+        if (m.type > NODE_PRINCIPLED) {
+            continue; // dead SparseStorage slot
+        }
+        // only the slots ShadeSurface reads for this node type are meaningful: AddMaterial zero-initialises material_t
+        // and leaves the others at 0 (SceneCPU.cpp:208-247); Mix keeps child material ids in slots 3/4
+        const int n_slots = (m.type == NODE_PRINCIPLED) ? 5 : 3;
+        for (int t = 0; t < n_slots; ++t) {
+            if (m.type == NODE_MIX && t != kTexBase) {
+                continue;
+            }
+            if (patch(m.textures[t], "material", i, t)) {
+                return 1;
             }
         }
     }
+    for (uint32_t i = 0; i < lts.size(); ++i) {
+        if ((lts[i].bits & 7u) == LIGHT_TRI) {
+            uint32_t h;
+            memcpy(&h, &lts[i].p[2], 4); // light_t::tri.tex_index
+            if (patch(h, "triangle light", i, 0)) {
+                return 1;
+            }
+            memcpy(&lts[i].p[2], &h, 4);
+        }
+    }
+    rc_scene_view patched = *sv;
+    patched.materials.ptr = mats.data();
+    patched.lights.ptr = lts.data();
+    sv = &patched;
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (upload_array(ctx, ctx->wnodes, sv->wnodes, sizeof(WNode), "wnodes") ||
         upload_array(ctx, ctx->mtris, sv->mtris, sizeof(MTri), "mtris") ||
@@ -809,7 +918,19 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
         upload_array(ctx, ctx->light_cwnodes, sv->light_cwnodes, sizeof(LightCWNode), "light_cwnodes")) {
         return 1;
     }
+    {
+        const rc_array da{descs.data(), uint32_t(descs.size()), uint32_t(sizeof(TexDesc))};
+        const rc_array ta{texels.data(), uint32_t(texels.size()), 4u};
+        if (upload_array(ctx, ctx->tex_descs, da, sizeof(TexDesc), "texture descriptors") ||
+            upload_array(ctx, ctx->tex_texels, ta, 4, "texels")) {
+            return 1;
+        }
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // descs / texels / mats / lts are locals
+    }
     ctx->scene_info = *sv;
+    ctx->scene_info.materials.ptr = nullptr;
+    ctx->scene_info.lights.ptr = nullptr;
+    ctx->scene_info.textures = nullptr;
     ctx->li_count = sv->li_indices.count;
     set_sort_bounds(ctx->sort, sv->bounds_min, sv->bounds_max);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1190,6 +1311,7 @@ int rc_abi_sizeof(int which) {
     case 3: return int(sizeof(rc_rect));
     case 4: return int(sizeof(rc_pass_desc));
     case 5: return int(sizeof(rc_counters));
+    case 6: return int(sizeof(rc_texture));
     default: return -1;
     }
 }

@@ -370,8 +370,23 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_closest(KParams 
                 const uint32_t rand_hash = hash_combine(px_hash, p.rand_seed);
                 const v2 mix_term_rand = rand2d(rand_dim + kRandDimBsdfPick, rand_hash, p.iteration - 1, p.sc.rand_seq);
                 float trans_r = mix_term_rand.x;
+                // alpha-textured Mix nodes (CoreRef.cpp:3088-3115): uvs at the hit + the bounce's texture jitter
+                v2 uvs = v2{0.0f, 0.0f}, tex_rand = v2{0.0f, 0.0f};
+                if (p.sc.tex.descs != nullptr && mat->type == NODE_MIX) {
+                    const Vertex &v1 = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 0]];
+                    const Vertex &v2_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 1]];
+                    const Vertex &v3_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 2]];
+                    const float w = 1.0f - inter.u - inter.v;
+                    uvs = v2{v1.t[0] * w + v2_.t[0] * inter.u + v3_.t[0] * inter.v,
+                             v1.t[1] * w + v2_.t[1] * inter.u + v3_.t[1] * inter.v};
+                    tex_rand = rand2d(rand_dim + kRandDimTex, rand_hash, p.iteration - 1, p.sc.rand_seq);
+                }
                 while (mat->type == NODE_MIX) {
-                    const float mix_val = mat->tangent_rotation_or_strength;
+                    float mix_val = mat->tangent_rotation_or_strength;
+                    const uint32_t mix_texture = mat->textures[kTexBase];
+                    if (mix_texture != kTexInvalid) {
+                        mix_val *= tex_sample_color(p.sc.tex, mix_texture, uvs, 0, tex_rand).x;
+                    }
                     if (trans_r > mix_val) {
                         mat = &p.sc.surf.materials[mat->textures[kMixMat1]];
                         trans_r = safe_div_pos(trans_r - mix_val, 1.0f - mix_val);
@@ -565,6 +580,7 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_shadow(KParams p
             v3 ro = r.o;
             v3 rc = r.c;
             int depth = transp_depth(r.depth);
+            uint32_t rand_dim = kRandDimBase + total_depth(r.depth) * kRandDimBounce;
             float dist = r.dist > 0.0f ? r.dist : kMaxDist;
             while (dist > kHitBias) {
                 Hit inter;
@@ -591,11 +607,27 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_shadow(KParams p
                 mstack[ms] = mat_index;
                 wstack[ms++] = 1.0f;
                 v3 throughput = v3{0.0f, 0.0f, 0.0f};
+                // alpha-textured Mix nodes (CoreRef.cpp:3203-3240)
+                v2 sh_uvs = v2{0.0f, 0.0f}, tex_rand = v2{0.0f, 0.0f};
+                if (p.sc.tex.descs != nullptr) {
+                    const Vertex &v1 = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 0]];
+                    const Vertex &v2_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 1]];
+                    const Vertex &v3_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 2]];
+                    const float w = 1.0f - inter.u - inter.v;
+                    sh_uvs = v2{v1.t[0] * w + v2_.t[0] * inter.u + v3_.t[0] * inter.v,
+                                v1.t[1] * w + v2_.t[1] * inter.u + v3_.t[1] * inter.v};
+                    tex_rand = rand2d(rand_dim + kRandDimTex, hash_combine(hash_u32(r.xy), p.rand_seed), p.iteration - 1,
+                                      p.sc.rand_seq);
+                }
                 while (ms--) {
                     const Material *mat = &p.sc.surf.materials[mstack[ms]];
                     const float weight = wstack[ms];
                     if (mat->type == NODE_MIX) {
-                        const float mix_val = mat->tangent_rotation_or_strength;
+                        float mix_val = mat->tangent_rotation_or_strength;
+                        const uint32_t mix_texture = mat->textures[kTexBase];
+                        if (mix_texture != kTexInvalid) {
+                            mix_val *= tex_sample_color(p.sc.tex, mix_texture, sh_uvs, 0, tex_rand).x;
+                        }
                         mstack[ms] = mat->textures[kMixMat1];
                         wstack[ms++] = weight * (1.0f - mix_val);
                         mstack[ms] = mat->textures[kMixMat2];
@@ -612,6 +644,7 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_shadow(KParams p
                 ro = ro + rd * t;
                 dist -= t;
                 ++depth;
+                rand_dim += kRandDimBounce;
             }
             if (p.sc.lights.blocker_lights_count != 0) {
                 rc *= intersect_area_lights_shadow(p.sc.lights, r.o, r.d, r.dist, st);

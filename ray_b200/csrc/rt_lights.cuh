@@ -9,6 +9,7 @@
 //   IntersectAreaLights(shadow, cwbvh) :4451-4592             EvalTriLightFactor(cwbvh)          :4692-4736
 #pragma once
 
+#include "rt_tex.cuh"
 #include "rt_traverse.cuh"
 
 namespace rt {
@@ -390,7 +391,8 @@ struct SceneSurf { // the arrays shading needs besides SceneGeo
 // SampleLightSource with hierarchical NEE (USE_HIERARCHICAL_NEE, USE_SPHERICAL_AREA_LIGHT_SAMPLING = true).
 // Textured lights / env maps are not supported by this backend (rc_upload_scene rejects them).
 RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, const SceneGeo &sg, const SceneSurf &ss,
-                                float rand_pick_light, v2 rand_light_uv, LightSample &ls) {
+                                const SceneTex &tx, float rand_pick_light, v2 rand_light_uv, v2 rand_tex_uv,
+                                LightSample &ls) {
     float u1 = rand_pick_light;
     float factor = 1.0f;
     uint32_t i = 0;
@@ -603,6 +605,7 @@ RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, co
         ls.area = 0.5f * light_fwd_len;
         ls.ray_flags = l_ray_visibility(l);
         v3 lp;
+        v2 luvs;
         float pdf = sample_spherical_triangle(P, p1, p2, p3, rand_light_uv, &ls.L);
         if (pdf > 0.0f) {
             const v3 pvec = cross(ls.L, e2);
@@ -610,8 +613,12 @@ RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, co
             const float inv_det = 1.0f / dot(e1, pvec);
             const float tri_u = dot(tvec, pvec) * inv_det, tri_v = dot(ls.L, qvec) * inv_det;
             lp = (1.0f - tri_u - tri_v) * p1 + tri_u * p2 + tri_v * p3;
+            const float w0 = 1.0f - tri_u - tri_v;
+            luvs = v2{w0 * v1.t[0] + tri_u * v2_.t[0] + tri_v * v3_.t[0], w0 * v1.t[1] + tri_u * v2_.t[1] + tri_v * v3_.t[1]};
         } else {
             const float r1 = sqrtf(rand_light_uv.x), r2 = rand_light_uv.y;
+            luvs = v2{v1.t[0] * (1.0f - r1) + r1 * (v2_.t[0] * (1.0f - r2) + v3_.t[0] * r2),
+                      v1.t[1] * (1.0f - r1) + r1 * (v2_.t[1] * (1.0f - r2) + v3_.t[1] * r2)};
             lp = p1 * (1.0f - r1) + r1 * (p2 * (1.0f - r2) + p3 * r2);
             float ls_dist;
             ls.L = normalize_len(lp - P, ls_dist);
@@ -625,6 +632,13 @@ RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, co
         }
         if (cos_theta > 0.0f) {
             ls.pdf = pdf;
+            const uint32_t tex_index = __float_as_uint(l.p[2]); // light_t::tri.tex_index
+            if (tex_index != kTexInvalid) {
+                const c4 tex_color = tex_sample_color(tx, tex_index, luvs, 0, rand_tex_uv);
+                ls.col.x *= tex_color.x;
+                ls.col.y *= tex_color.y;
+                ls.col.z *= tex_color.z;
+            }
         }
     } else if (type == LIGHT_ENV) {
         // no env map => no quad-tree (SceneCPU.cpp:905-908): sample the hemisphere around N

@@ -36,6 +36,10 @@ struct v2 {
 struct v3 {
     float x, y, z;
 };
+
+struct c4 { // rgb + a 4th lane (pdf for BSDF results, alpha for pixel colours)
+    float x, y, z, w;
+};
 struct v4 {
     float x, y, z, w;
 };

@@ -42,12 +42,10 @@ struct ShadowRayD { // Ref::shadow_ray_t in registers
     uint32_t xy;
 };
 
-struct c4 { // rgb + a 4th lane (pdf for BSDF results, alpha for pixel colours)
-    float x, y, z, w;
-};
 
 struct Surface {
     v3 P, T, B, N, plane_N;
+    v2 uvs;
 };
 
 RT_FN v2 calc_alpha(float roughness, float anisotropy, float regularize_alpha) {
@@ -412,6 +410,7 @@ struct ShadeScene {
     SceneGeo geo;
     SceneSurf surf;
     SceneLights lights;
+    SceneTex tex;
     const uint32_t *__restrict__ rand_seq;
     uint32_t li_count; // li_indices.size()
 };
@@ -427,6 +426,46 @@ struct ShadeOut {
     float aov_depth;
     bool wrote_aov;
 };
+
+// ensure_valid_reflection (ShadeRef.cpp:237-333, "taken from Cycles"): only normal-mapped surfaces reach it
+RT_FN v3 ensure_valid_reflection(v3 Ng, v3 I, v3 N) {
+    const v3 R = (2.0f * dot(N, I)) * N - I;
+    const float threshold = fminf(0.9f * dot(Ng, I), 0.01f);
+    if (dot(Ng, R) >= threshold) {
+        return N;
+    }
+    const float NdotNg = dot(N, Ng);
+    const v3 X = normalize(N - NdotNg * Ng);
+    const float Ix = dot(I, X), Iz = dot(I, Ng);
+    const float Ix2 = (Ix * Ix), Iz2 = (Iz * Iz);
+    const float a = Ix2 + Iz2;
+    const float b = safe_sqrt(Ix2 * (a - (threshold * threshold)));
+    const float c = Iz * threshold + a;
+    const float fac = 0.5f / a;
+    const float N1_z2 = fac * (b + c), N2_z2 = fac * (-b + c);
+    bool valid1 = (N1_z2 > 1e-5f) && (N1_z2 <= (1.0f + 1e-5f));
+    bool valid2 = (N2_z2 > 1e-5f) && (N2_z2 <= (1.0f + 1e-5f));
+    v2 N_new;
+    if (valid1 && valid2) {
+        const v2 N1 = v2{safe_sqrt(1.0f - N1_z2), safe_sqrt(N1_z2)};
+        const v2 N2 = v2{safe_sqrt(1.0f - N2_z2), safe_sqrt(N2_z2)};
+        const float R1 = 2 * (N1.x * Ix + N1.y * Iz) * N1.y - Iz;
+        const float R2 = 2 * (N2.x * Ix + N2.y * Iz) * N2.y - Iz;
+        valid1 = (R1 >= 1e-5f);
+        valid2 = (R2 >= 1e-5f);
+        if (valid1 && valid2) {
+            N_new = (R1 < R2) ? N1 : N2;
+        } else {
+            N_new = (R1 > R2) ? N1 : N2;
+        }
+    } else if (valid1 || valid2) {
+        const float Nz2 = valid1 ? N1_z2 : N2_z2;
+        N_new = v2{safe_sqrt(1.0f - Nz2), safe_sqrt(Nz2)};
+    } else {
+        return Ng;
+    }
+    return N_new.x * X + N_new.y * Ng;
+}
 
 // Everything a material-node branch of ShadeSurface reads or writes.  The branches are separate (non-inlined) functions
 // so the kernel's hot instruction footprint is the branch actually taken, not all five (see RT_FN in rt_math.cuh).
@@ -455,6 +494,8 @@ struct MatCtx {
     uint32_t rand_dim, rand_hash;
     float term_rand_y, cone_width;
     int iteration;
+    float lambda; // ray-cone texture LOD term (ShadeRef.cpp:1279-1284)
+    v2 tex_rand;
 };
 
 RT_FN void shade_node_diffuse(MatCtx &c) {
@@ -731,8 +772,16 @@ RT_FN void shade_node_principled(MatCtx &c) {
     (void)roughness; (void)mix_weight; (void)mix_rand; (void)regularize_alpha; (void)ext_ior; (void)base_color_lum;
     (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
     (void)tri_index; (void)tl_stack; (void)tl_factors;
-    const float metallic = unorm16(mat->metallic_unorm);
-    const float specular = unorm16(mat->specular_unorm);
+    float metallic = unorm16(mat->metallic_unorm);
+    if (mat->textures[kTexMetallic] != kTexInvalid) { // ShadeRef.cpp:1540-1545 (no colour-space conversion)
+        const uint32_t metallic_tex = mat->textures[kTexMetallic];
+        metallic *= tex_unpack(tex_sample_bytes(sc.tex, metallic_tex, surf.uvs, tex_lod(sc.tex, metallic_tex, c.lambda), c.tex_rand)).x;
+    }
+    float specular = unorm16(mat->specular_unorm);
+    if (mat->textures[kTexSpecular] != kTexInvalid) { // ShadeRef.cpp:1547-1557
+        const uint32_t specular_tex = mat->textures[kTexSpecular];
+        specular *= tex_sample_color(sc.tex, specular_tex, surf.uvs, tex_lod(sc.tex, specular_tex, c.lambda), c.tex_rand).x;
+    }
     const float specular_tint = unorm16(mat->specular_tint_unorm);
     const float transmission = unorm16(mat->transmission_unorm);
     const float clearcoat = unorm16(mat->clearcoat_unorm);
@@ -1064,6 +1113,7 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
 
     const float w = 1.0f - inter.u - inter.v;
     surf.N = normalize(mk3(v1.n) * w + mk3(v2_.n) * inter.u + mk3(v3_.n) * inter.v);
+    surf.uvs = v2{v1.t[0] * w + v2_.t[0] * inter.u + v3_.t[0] * inter.v, v1.t[1] * w + v2_.t[1] * inter.u + v3_.t[1] * inter.v};
 
     float pa;
     // fvec4{v.p} loads 4 floats (p.xyz, n.x); the 4th lane of the cross product is set to 0 by cross()
@@ -1096,7 +1146,17 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     surf.T = safe_normalize(surf.T);
 
     const float cone_width = ray.cone_width + ray.cone_spread * inter.t;
-    // (texture LOD `lambda` is only consumed by texture fetches, which this backend does not have)
+    // texture LOD term and jitter: only consumed by texture fetches (pure functions of the inputs, so skipping them for
+    // untextured scenes changes nothing)
+    const bool has_tex = sc.tex.descs != nullptr;
+    float lambda = 0.0f;
+    v2 tex_rand = v2{0.0f, 0.0f};
+    if (has_tex) {
+        const float ta = fabsf((v2_.t[0] - v1.t[0]) * (v3_.t[1] - v1.t[1]) - (v3_.t[0] - v1.t[0]) * (v2_.t[1] - v1.t[1]));
+        lambda = 0.5f * fast_log2(ta / pa);
+        lambda += fast_log2(cone_width);
+        tex_rand = rand2d(rand_dim + kRandDimTex, rand_hash, iteration - 1, sc.rand_seq);
+    }
 
     const float ext_ior = peek_ior_stack(ray.ior, is_backfacing);
 
@@ -1113,6 +1173,10 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     // resolve mix material
     while (mat->type == NODE_MIX) {
         float mix_val = mat->tangent_rotation_or_strength;
+        const uint32_t mix_texture = mat->textures[kTexBase];
+        if (mix_texture != kTexInvalid) {
+            mix_val *= tex_sample_color(sc.tex, mix_texture, surf.uvs, 0, tex_rand).x;
+        }
         const float eta = is_backfacing ? safe_div_pos(ext_ior, mat->ior) : safe_div_pos(mat->ior, ext_ior);
         const float RR = mat->ior != 0.0f ? fresnel_dielectric_cos(dot(I, surf.N), eta) : 1.0f;
         mix_val *= saturatef(RR);
@@ -1125,6 +1189,23 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
             mat = &sc.surf.materials[mat->textures[kMixMat2]];
             mix_rand = safe_div_pos(mix_rand, mix_val);
         }
+    }
+
+    // apply normal map (ShadeRef.cpp:1335-1349)
+    if (mat->textures[kTexNormals] != kTexInvalid) {
+        const uint32_t nh = mat->textures[kTexNormals];
+        const c4 nc = tex_unpack(tex_sample_bytes(sc.tex, nh, surf.uvs, 0, tex_rand));
+        const float nx = nc.x * 2.0f - 1.0f, ny = nc.y * 2.0f - 1.0f;
+        float nz = 1.0f;
+        if (nh & kTexReconstructZBit) {
+            nz = safe_sqrt(1.0f - nx * nx - ny * ny);
+        }
+        const v3 in_normal = surf.N;
+        surf.N = normalize(nx * surf.T + nz * surf.N + ny * surf.B);
+        if (mat->normal_map_strength_unorm != 0xffff) {
+            surf.N = normalize(in_normal + (surf.N - in_normal) * unorm16(mat->normal_map_strength_unorm));
+        }
+        surf.N = ensure_valid_reflection(surf.plane_N, -I, surf.N);
     }
 
     { // radial tangent in local space
@@ -1183,6 +1264,8 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     c.term_rand_y = mix_term_rand.y;
     c.cone_width = cone_width;
     c.iteration = iteration;
+    c.lambda = lambda;
+    c.tex_rand = tex_rand;
     return true;
 }
 
@@ -1201,8 +1284,8 @@ RT_DEV void shade_surface_l(MatCtx &c) {
         const float rand_pick_light =
             rand2d(c.rand_dim + kRandDimLightPick, c.rand_hash, c.iteration - 1, sc.rand_seq).x;
         const v2 rand_light_uv = rand2d(c.rand_dim + kRandDimLight, c.rand_hash, c.iteration - 1, sc.rand_seq);
-        sample_light_source(surf.P, surf.T, surf.B, surf.N, sc.lights, sc.geo, sc.surf, rand_pick_light, rand_light_uv,
-                            ls);
+        sample_light_source(surf.P, surf.T, surf.B, surf.N, sc.lights, sc.geo, sc.surf, sc.tex, rand_pick_light,
+                            rand_light_uv, c.tex_rand, ls);
     }
 }
 
@@ -1221,7 +1304,14 @@ RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
     v3 col = c.col;
     const float N_dot_L = dot(surf.N, ls.L);
 
-    const v3 base_color = mk3(mat->base_color);
+    v3 base_color = mk3(mat->base_color);
+    if (mat->textures[kTexBase] != kTexInvalid) { // ShadeRef.cpp:1405-1419
+        const uint32_t base_texture = mat->textures[kTexBase];
+        const c4 tex_color = tex_sample_color(sc.tex, base_texture, surf.uvs, tex_lod(sc.tex, base_texture, c.lambda), c.tex_rand);
+        base_color.x *= tex_color.x;
+        base_color.y *= tex_color.y;
+        base_color.z *= tex_color.z;
+    }
     out.base_color = base_color;
     out.aov_normal = surf.N;
     out.aov_depth = inter.t;
@@ -1233,7 +1323,11 @@ RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
         tint_color = base_color / base_color_lum;
     }
 
-    const float roughness = unorm16(mat->roughness_unorm);
+    float roughness = unorm16(mat->roughness_unorm);
+    if (mat->textures[kTexRough] != kTexInvalid) { // ShadeRef.cpp:1440-1449
+        const uint32_t roughness_tex = mat->textures[kTexRough];
+        roughness *= tex_sample_color(sc.tex, roughness_tex, surf.uvs, tex_lod(sc.tex, roughness_tex, c.lambda), c.tex_rand).x;
+    }
 
     const v2 rand_bsdf = rand2d(rand_dim + kRandDimBsdf, rand_hash, iteration - 1, sc.rand_seq);
 

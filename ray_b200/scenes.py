@@ -43,6 +43,11 @@ class SceneDesc:
     back_col: tuple = (0.0, 0.0, 0.0)
     env_importance_sample: bool = True
     camera: capi.rs_camera_desc = None
+    textures: list = field(default_factory=list)  # (uint8 array (h, w, c), flags dict); material descs refer by index
+
+    def add_texture(self, pixels, **flags):
+        self.textures.append((np.ascontiguousarray(pixels, dtype=np.uint8), flags))
+        return len(self.textures) - 1
 
     def add_node(self, **kw):
         self.materials.append(("node", capi.rs_shading_node_desc.default(**kw)))
@@ -59,17 +64,29 @@ class SceneDesc:
 def build(desc: SceneDesc, backend):
     """Replay `desc` on `backend`; returns the backend (finalized)."""
     backend.set_environment(desc.env_col, desc.back_col, desc.env_importance_sample)
+    tex_ids = [backend.add_texture(px, **flags) for px, flags in desc.textures]
+
+    def with_textures(d, fields):
+        """texture fields hold indices into desc.textures -> translate to backend handles (on a copy)"""
+        d2 = type(d).from_buffer_copy(d)
+        for f in fields:
+            v = getattr(d, f)
+            if v != capi.RS_INVALID:
+                setattr(d2, f, tex_ids[v])
+        return d2
+
     mat_ids = []
     for kind, d in desc.materials:
         if kind == "node":
+            d = with_textures(d, ("base_texture", "normal_map", "roughness_texture", "metallic_texture"))
             # mix children refer to indices in desc.materials -> translate to backend handles
             if d.type == capi.NODE_MIX:
-                d2 = capi.rs_shading_node_desc.from_buffer_copy(d)
-                d2.mix_materials[0] = mat_ids[d.mix_materials[0]]
-                d2.mix_materials[1] = mat_ids[d.mix_materials[1]]
-                d = d2
+                d.mix_materials[0] = mat_ids[d.mix_materials[0]]
+                d.mix_materials[1] = mat_ids[d.mix_materials[1]]
             mat_ids.append(backend.add_material_node(d))
         else:
+            d = with_textures(d, ("base_texture", "metallic_texture", "specular_texture", "roughness_texture",
+                                  "emission_texture", "alpha_texture", "normal_map"))
             mat_ids.append(backend.add_material_principled(d))
     mesh_ids = []
     for m in desc.meshes:
@@ -433,4 +450,93 @@ def material_zoo(width=160, height=120, lights=("rect", "sphere", "dir", "spot",
     s.camera = capi.rs_camera_desc.default(origin=(0.0, 2.6, 7.5), fwd=tuple(fwd.astype(np.float32)), fov=42.0,
                                            filter=filter, max_diff_depth=4, max_total_depth=8, fstop=fstop,
                                            focus_distance=7.5, focal_length=0.05 if fstop > 0 else 0.0)
+    return s
+
+
+def _checker(n, cells, a, b, channels=3):
+    y, x = np.mgrid[0:n, 0:n]
+    m = (((x * cells) // n + (y * cells) // n) & 1).astype(bool)
+    img = np.where(m[..., None], np.asarray(a, np.uint8), np.asarray(b, np.uint8)).astype(np.uint8)
+    return img if channels > 1 else img[..., 0]
+
+
+def textured(width=96, height=72) -> SceneDesc:
+    """Every place the reference fetches a texture on the path: sRGB base colour (RGB and
+    RGBA storages), linear roughness / metallic / specular maps (R8), a tangent-space normal map (RG storage with
+    reconstructed z, intensity < 1), an alpha-textured principled material (Mix with a Transparent node: the transparency
+    loops of the closest-hit and shadow traces), a Mix node driven by a texture, and a textured emissive quad sampled
+    through the light tree."""
+    s = SceneDesc(name="textured", width=width, height=height)
+    rng = np.random.RandomState(11)
+    n = 64
+    t_checker = s.add_texture(_checker(n, 8, (230, 220, 200), (40, 60, 120)), is_srgb=True)
+    noise = rng.randint(0, 256, size=(n, n, 4)).astype(np.uint8)
+    noise[..., 3] = 255
+    t_rgba = s.add_texture(noise, is_srgb=True)
+    yy, xx = np.mgrid[0:n, 0:n]
+    t_rough = s.add_texture((40 + 180 * ((xx // 8) % 2)).astype(np.uint8), is_srgb=False)
+    t_metal = s.add_texture((255 * ((yy // 16) % 2)).astype(np.uint8), is_srgb=False)
+    t_spec = s.add_texture(rng.randint(64, 256, size=(n, n)).astype(np.uint8), is_srgb=True)
+    nx = 0.35 * np.sin(xx * (2 * np.pi / 16.0))
+    ny = 0.35 * np.cos(yy * (2 * np.pi / 12.0))
+    nz = np.sqrt(np.maximum(1.0 - nx * nx - ny * ny, 0.0))
+    nm = np.stack([(nx * 0.5 + 0.5) * 255, (ny * 0.5 + 0.5) * 255, (nz * 0.5 + 0.5) * 255], axis=-1)
+    t_normal = s.add_texture(np.round(nm).astype(np.uint8), is_srgb=False, is_normalmap=True)
+    disk = (((xx - n / 2) ** 2 + (yy - n / 2) ** 2) < (n * 0.38) ** 2)
+    t_alpha = s.add_texture((255 * disk).astype(np.uint8), is_srgb=False)
+    t_mix = s.add_texture(_checker(n, 4, (255,), (0,), channels=1), is_srgb=False)
+    emit = np.zeros((n, n, 3), np.uint8)
+    emit[..., 0] = 255 * ((xx // 16) % 2)
+    emit[..., 1] = 200
+    emit[..., 2] = 255 * ((yy // 16) % 2)
+    t_emit = s.add_texture(emit, is_srgb=True)
+
+    m_floor = s.add_node(type=capi.NODE_DIFFUSE, base_color=(0.9, 0.9, 0.9), base_texture=t_checker)
+    mats = [
+        s.add_principled(base_color=(1.0, 1.0, 1.0), base_texture=t_rgba, roughness=0.8, roughness_texture=t_rough),
+        s.add_principled(base_color=(0.9, 0.7, 0.3), metallic=1.0, metallic_texture=t_metal, roughness=0.3,
+                         specular=0.8, specular_texture=t_spec),
+        s.add_principled(base_color=(0.3, 0.6, 0.3), roughness=0.4, normal_map=t_normal, normal_map_intensity=0.7),
+        s.add_node(type=capi.NODE_GLOSSY, base_color=(0.9, 0.9, 0.9), roughness=0.5, roughness_texture=t_rough,
+                   normal_map=t_normal),
+    ]
+    d0 = s.add_node(type=capi.NODE_DIFFUSE, base_color=(0.8, 0.2, 0.2))
+    g0 = s.add_node(type=capi.NODE_GLOSSY, base_color=(0.9, 0.9, 0.9), roughness=0.05)
+    mats.append(s.add_node(type=capi.NODE_MIX, mix_materials=(d0, g0), strength=1.0, base_texture=t_mix))
+    m_cutout = s.add_principled(base_color=(0.9, 0.8, 0.2), base_texture=t_checker, roughness=0.5, alpha=1.0,
+                                alpha_texture=t_alpha)
+    m_light = s.add_node(type=capi.NODE_EMISSIVE, strength=14.0, base_color=(1.0, 1.0, 1.0), base_texture=t_emit,
+                         importance_sample=1)
+
+    def sph(u, v):
+        th = np.pi * (0.01 + 0.98 * v)
+        ph = 2 * np.pi * u
+        r = 0.45
+        return r * np.sin(th) * np.cos(ph), r * np.cos(th), r * np.sin(th) * np.sin(ph)
+
+    sa, si = _grid_mesh(16, 12, sph, flip=True)
+    sa = sa.copy()
+    sa[:, 6] *= 3.0  # tile the textures 3x around the sphere
+    sa[:, 7] *= 2.0
+    for m in mats:
+        s.meshes.append(MeshDesc(sa, si, [(m, m, 0, len(si))]))
+    ga, gi = _flat_quad((-5, 0, -4), (-5, 0, 4), (5, 0, 4), (5, 0, -4), (0, 1, 0))
+    ga = ga.copy()
+    ga[:, 6:8] *= 2.5
+    la, li = _flat_quad((-1.0, 3.0, -1.0), (1.0, 3.0, -1.0), (1.0, 3.0, 0.0), (-1.0, 3.0, 0.0), (0, -1, 0))
+    ca, ci = _flat_quad((-1.2, 0.2, 1.6), (1.2, 0.2, 1.6), (1.2, 1.8, 1.6), (-1.2, 1.8, 1.6), (0, 0, 1))
+    s.meshes.append(MeshDesc(np.concatenate([ga, la, ca]), np.concatenate([gi, li + np.uint32(4), ci + np.uint32(8)]),
+                             [(m_floor, m_floor, 0, 6), (m_light, capi.RS_INVALID, 6, 6), (m_cutout, m_cutout, 12, 6)]))
+    k = len(mats)
+    for i in range(k):
+        M = np.eye(4)
+        M[:3, 3] = [(i - (k - 1) / 2) * 1.15, 0.5, 0.2 * np.cos(i * 1.7)]
+        s.instances.append((i, M.T.astype(np.float32).reshape(16), {}))
+    s.instances.append((k, IDENTITY.T.reshape(16), {}))
+    s.lights.append(("sphere", capi.rs_sphere_light_desc(c=capi.rs_light_common.default(color=(15.0, 15.0, 18.0)),
+                                                         position=(2.5, 2.5, 2.0), radius=0.15)))
+    fwd = np.array([0.0, -0.30, -1.0])
+    fwd /= np.linalg.norm(fwd)
+    s.camera = capi.rs_camera_desc.default(origin=(0.0, 2.2, 6.5), fwd=tuple(fwd.astype(np.float32)), fov=40.0,
+                                           filter=capi.FILTER_BOX, max_diff_depth=4, max_total_depth=8)
     return s

@@ -35,6 +35,7 @@ def load():
         "ro_cpu_features": (C.c_int, []),
         "ro_scene_create": (vp, [C.c_int]),
         "ro_scene_destroy": (None, [vp]),
+        "ro_add_texture": (C.c_uint32, [vp, P(capi.rs_tex_desc)]),
         "ro_add_material_node": (C.c_uint32, [vp, P(capi.rs_shading_node_desc)]),
         "ro_add_material_principled": (C.c_uint32, [vp, P(capi.rs_principled_mat_desc)]),
         "ro_add_mesh": (C.c_uint32, [vp, P(capi.rs_mesh_desc)]),
@@ -112,6 +113,11 @@ class Scene:
         d = capi.rs_environment_desc(env_col=tuple(env_col), back_col=tuple(back_col),
                                      importance_sample=1 if importance_sample else 0)
         self.lib.ro_set_environment(self.h, C.byref(d))
+
+    def add_texture(self, pixels, is_srgb=True, is_normalmap=False, generate_mipmaps=False, reconstruct_z=False,
+                    convention=0):
+        d, keep = capi.make_tex_desc(pixels, is_srgb, is_normalmap, generate_mipmaps, reconstruct_z, convention)
+        return self.lib.ro_add_texture(self.h, C.byref(d))
 
     def add_material_node(self, d):
         return self.lib.ro_add_material_node(self.h, C.byref(d))

@@ -43,7 +43,7 @@ def test_ray_host_exports_every_declared_symbol():
 def test_struct_sizes_match_ctypes_mirrors():
     lc, lh = cuda.load_library(), host.load_library()
     for i, t in enumerate([capi.rc_array, capi.rc_scene_view, capi.rc_camera, capi.rc_rect, capi.rc_pass_desc,
-                           capi.rc_counters]):
+                           capi.rc_counters, capi.rc_texture]):
         assert lc.rc_abi_sizeof(i) == C.sizeof(t), t.__name__
     for i, t in enumerate([capi.rs_shading_node_desc, capi.rs_principled_mat_desc, capi.rs_mat_group_desc,
                            capi.rs_vtx_attribute, capi.rs_mesh_desc, capi.rs_mesh_instance_desc, capi.rs_light_common,

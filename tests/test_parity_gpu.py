@@ -20,6 +20,9 @@ SCENES = {
     "instanced": lambda: scenes.instanced(36, 600, 128, 96),
     "hall_small": lambda: scenes.hall("principled", 160, 90, floor_res=48, n_columns=8, col_seg=12, col_rings=8,
                                       extra_lights=12),
+    # every texture fetch on the path (base / roughness / metallic / specular / normal maps,
+    # texture-driven Mix, alpha cut-out through the transparency loops, textured emissive triangles)
+    "textured": lambda: scenes.textured(96, 72),
 }
 
 
