@@ -33,6 +33,8 @@ void rh_clear(rh_renderer *r, const float rgba[4]);
 rh_scene *rh_create_scene(rh_renderer *r);
 void rh_destroy_scene(rh_scene *s);
 void rh_set_environment(rh_scene *s, const rs_environment_desc *d);
+/* SceneBase::AddTexture (SceneBase.h:392): returns TextureHandle::_index for the texture fields of the material descs */
+uint32_t rh_add_texture(rh_scene *s, const rs_tex_desc *d);
 uint32_t rh_add_material_node(rh_scene *s, const rs_shading_node_desc *d);
 uint32_t rh_add_material_principled(rh_scene *s, const rs_principled_mat_desc *d);
 uint32_t rh_add_mesh(rh_scene *s, const rs_mesh_desc *d);

@@ -131,9 +131,7 @@ using disk_light_desc_t = rs_disk_light_desc;
 using line_light_desc_t = rs_line_light_desc;
 using camera_desc_t = rs_camera_desc;
 using environment_desc_t = rs_environment_desc;
-struct tex_desc_t {
-    int w = 0, h = 0;
-};
+using tex_desc_t = rs_tex_desc; // tex_desc_t, SceneBase.h:177-192 (uncompressed formats)
 
 class SceneBase { // reference SceneBase.h:371-516
   protected:

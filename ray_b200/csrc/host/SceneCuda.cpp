@@ -209,23 +209,78 @@ void Scene::SetEnvironment(const environment_desc_t &env) {
     env_ = env;
 }
 
-TextureHandle Scene::AddTexture(const tex_desc_t &) {
-    log_->Error("Ray(CUDA): textures are not supported by the CUDA backend");
-    return TextureHandle{};
+// reference SceneCPU.cpp:61-205 with texture compression off: RGBA -> storage 0, RGB -> 1, RG and every normal map -> 2
+// (x, y kept, y inverted for the DX convention, z reconstructed when the map's z is not a constant 1), R -> 3.
+// The uncompressed storages never build mips (TextureStorageCPU.cpp:232), so generate_mipmaps is accepted and ignored.
+TextureHandle Scene::AddTexture(const tex_desc_t &t) {
+    if (!t.data || t.w <= 0 || t.h <= 0 || t.w > 65535 || t.h > 65535) {
+        log_->Error("Ray(CUDA): AddTexture: bad texture description");
+        return TextureHandle{};
+    }
+    const size_t n = size_t(t.w) * t.h;
+    bool reconstruct_z = t.reconstruct_z != 0;
+    const bool invert_y = (t.convention == 1);
+    TexImage img;
+    img.w = t.w;
+    img.h = t.h;
+    int storage = -1;
+    if (t.format == RS_TEX_RGBA8888 || t.format == RS_TEX_RGB888) {
+        const int c = (t.format == RS_TEX_RGBA8888) ? 4 : 3;
+        if (!t.is_normalmap) {
+            storage = (c == 4) ? 0 : 1;
+            img.channels = uint32_t(c);
+            img.pixels.assign(t.data, t.data + n * c);
+        } else {
+            storage = 2;
+            img.channels = 2;
+            img.pixels.resize(n * 2);
+            for (size_t i = 0; i < n; ++i) {
+                img.pixels[i * 2 + 0] = t.data[i * c + 0];
+                img.pixels[i * 2 + 1] = invert_y ? uint8_t(255 - t.data[i * c + 1]) : t.data[i * c + 1];
+                reconstruct_z |= (t.data[i * c + 2] < 250);
+            }
+        }
+    } else if (t.format == RS_TEX_RG88) {
+        storage = 2;
+        img.channels = 2;
+        img.pixels.assign(t.data, t.data + n * 2);
+        if (t.is_normalmap && invert_y) {
+            for (size_t i = 0; i < n; ++i) {
+                img.pixels[i * 2 + 1] = uint8_t(255 - img.pixels[i * 2 + 1]);
+            }
+        }
+        reconstruct_z = t.is_normalmap != 0;
+    } else if (t.format == RS_TEX_R8) {
+        storage = 3;
+        img.channels = 1;
+        img.pixels.assign(t.data, t.data + n);
+    } else {
+        log_->Error("Ray(CUDA): AddTexture: format %u is not supported (uncompressed RGBA/RGB/RG/R only)", t.format);
+        return TextureHandle{};
+    }
+    std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    const uint32_t index = tex_storage_counts_[storage]++;
+    img.handle = (uint32_t(storage) << 28) | index;
+    uint32_t ret = img.handle;
+    if (t.is_srgb) {
+        ret |= rt::kTexSrgbBitHost;
+    }
+    if (reconstruct_z) {
+        ret |= rt::kTexReconstructZBitHost;
+    }
+    textures_.push_back(std::move(img));
+    ++revision_;
+    return TextureHandle{ret, 0};
 }
 
 // reference SceneCPU.cpp:208-250
 MaterialHandle Scene::AddMaterial_nolock(const shading_node_desc_t &m) {
-    if (m.base_texture != RS_INVALID || m.normal_map != RS_INVALID || m.roughness_texture != RS_INVALID ||
-        m.metallic_texture != RS_INVALID) {
-        log_->Error("Ray(CUDA): material uses textures; textures are not supported by the CUDA backend");
-    }
     rt::Material mat;
     memset(&mat, 0, sizeof(mat));
     mat.type = m.type;
-    mat.textures[rt::kTexBase] = 0xffffffffu;
+    mat.textures[rt::kTexBase] = m.base_texture;
     mat.roughness_unorm = pack_unorm_16(clampf(m.roughness, 0.0f, 1.0f));
-    mat.textures[rt::kTexRough] = 0xffffffffu;
+    mat.textures[rt::kTexRough] = m.roughness_texture;
     memcpy(mat.base_color, m.base_color, 3 * sizeof(float));
     mat.ior = m.ior;
     mat.tangent_rotation_or_strength = 0.0f;
@@ -233,10 +288,10 @@ MaterialHandle Scene::AddMaterial_nolock(const shading_node_desc_t &m) {
     if (m.type == rt::NODE_DIFFUSE) {
         mat.sheen_unorm = pack_unorm_16(clampf(0.5f * m.sheen, 0.0f, 1.0f));
         mat.sheen_tint_unorm = pack_unorm_16(clampf(m.tint, 0.0f, 1.0f));
-        mat.textures[rt::kTexMetallic] = 0xffffffffu;
+        mat.textures[rt::kTexMetallic] = m.metallic_texture;
     } else if (m.type == rt::NODE_GLOSSY) {
         mat.tangent_rotation_or_strength = 2.0f * PI * m.anisotropic_rotation;
-        mat.textures[rt::kTexMetallic] = 0xffffffffu;
+        mat.textures[rt::kTexMetallic] = m.metallic_texture;
         mat.tint_unorm = pack_unorm_16(clampf(m.tint, 0.0f, 1.0f));
     } else if (m.type == rt::NODE_EMISSIVE) {
         mat.tangent_rotation_or_strength = m.strength;
@@ -251,7 +306,7 @@ MaterialHandle Scene::AddMaterial_nolock(const shading_node_desc_t &m) {
             mat.flags |= rt::kMatFlagMixAdd;
         }
     }
-    mat.textures[rt::kTexNormals] = 0xffffffffu;
+    mat.textures[rt::kTexNormals] = m.normal_map;
     mat.normal_map_strength_unorm = pack_unorm_16(clampf(m.normal_map_intensity, 0.0f, 1.0f));
     materials_.push_back(mat);
     return MaterialHandle{uint32_t(materials_.size() - 1), 0};
@@ -264,17 +319,14 @@ MaterialHandle Scene::AddMaterial(const shading_node_desc_t &m) {
 
 // reference SceneCPU.cpp:252-340: principled root (+ emissive via additive mix, + transparent via alpha mix)
 MaterialHandle Scene::AddMaterial(const principled_mat_desc_t &m) {
-    if (m.base_texture != RS_INVALID || m.metallic_texture != RS_INVALID || m.specular_texture != RS_INVALID ||
-        m.roughness_texture != RS_INVALID || m.emission_texture != RS_INVALID || m.alpha_texture != RS_INVALID ||
-        m.normal_map != RS_INVALID) {
-        log_->Error("Ray(CUDA): material uses textures; textures are not supported by the CUDA backend");
-    }
     rt::Material mm;
     memset(&mm, 0, sizeof(mm));
     mm.type = rt::NODE_PRINCIPLED;
-    for (int i = 0; i < 5; ++i) {
-        mm.textures[i] = 0xffffffffu;
-    }
+    mm.textures[rt::kTexBase] = m.base_texture;
+    mm.textures[rt::kTexRough] = m.roughness_texture;
+    mm.textures[rt::kTexMetallic] = m.metallic_texture;
+    mm.textures[rt::kTexNormals] = m.normal_map;
+    mm.textures[rt::kTexSpecular] = m.specular_texture;
     memcpy(mm.base_color, m.base_color, 3 * sizeof(float));
     mm.sheen_unorm = pack_unorm_16(clampf(0.5f * m.sheen, 0.0f, 1.0f));
     mm.sheen_tint_unorm = pack_unorm_16(clampf(m.sheen_tint, 0.0f, 1.0f));
@@ -302,11 +354,12 @@ MaterialHandle Scene::AddMaterial(const principled_mat_desc_t &m) {
         rs_shading_node_defaults(&e);
         e.type = rt::NODE_EMISSIVE;
         memcpy(e.base_color, m.emission_color, 3 * sizeof(float));
+        e.base_texture = m.emission_texture;
         e.strength = m.emission_strength;
         e.importance_sample = m.importance_sample;
         emissive = AddMaterial_nolock(e);
     }
-    if (m.alpha != 1.0f) {
+    if (m.alpha != 1.0f || m.alpha_texture != RS_INVALID) {
         shading_node_desc_t t;
         rs_shading_node_defaults(&t);
         t.type = rt::NODE_TRANSPARENT;
@@ -330,6 +383,7 @@ MaterialHandle Scene::AddMaterial(const principled_mat_desc_t &m) {
             shading_node_desc_t mix;
             rs_shading_node_defaults(&mix);
             mix.type = rt::NODE_MIX;
+            mix.base_texture = m.alpha_texture;
             mix.strength = m.alpha;
             mix.ior = 0.0f;
             mix.mix_materials[0] = transparent._index;
@@ -700,7 +754,7 @@ MeshInstanceHandle Scene::AddMeshInstance(const mesh_instance_desc_t &d) {
             l.bits = light_bits(rt::LIGHT_TRI, be != 0xffffffffu, true, false, false, vis);
             l.p[0] = u2f(tri);
             l.p[1] = u2f(mi_index);
-            l.p[2] = u2f(0xffffffffu);
+            l.p[2] = u2f(mat.textures[rt::kTexBase]); // tri.tex_index (SceneCPU.cpp:840)
             l.col[0] = mat.base_color[0] * mat.tangent_rotation_or_strength;
             l.col[1] = mat.base_color[1] * mat.tangent_rotation_or_strength;
             l.col[2] = mat.base_color[2] * mat.tangent_rotation_or_strength;
@@ -1210,6 +1264,20 @@ void Scene::FillView(rc_scene_view &v) const {
     v.sky_map_spread_angle = 0.0f;
     memcpy(v.bounds_min, bounds_min_, sizeof(v.bounds_min));
     memcpy(v.bounds_max, bounds_max_, sizeof(v.bounds_max));
+    tex_views_.clear();
+    for (const TexImage &img : textures_) {
+        rc_texture t = {};
+        t.handle = img.handle;
+        t.channels = img.channels;
+        for (int lod = 0; lod < RC_TEX_MIP_LEVELS; ++lod) { // no mips: every level aliases level 0
+            t.res[lod][0] = uint16_t(img.w);
+            t.res[lod][1] = uint16_t(img.h);
+            t.pixels[lod] = img.pixels.data();
+        }
+        tex_views_.push_back(t);
+    }
+    v.textures = tex_views_.empty() ? nullptr : tex_views_.data();
+    v.texture_count = uint32_t(tex_views_.size());
 }
 
 } // namespace Cuda

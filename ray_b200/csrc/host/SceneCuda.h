@@ -29,6 +29,15 @@ class Scene final : public SceneBase {
     friend class Renderer;
     mutable std::shared_timed_mutex mtx_;
 
+    struct TexImage { // one texture of one of the four uncompressed storages (SceneCPU.h:65-68), no mips
+        uint32_t handle;   // (storage << 28) | index
+        uint32_t channels; // 4, 3, 2, 1 for storages 0..3
+        int w, h;
+        std::vector<uint8_t> pixels;
+    };
+    std::vector<TexImage> textures_;
+    uint32_t tex_storage_counts_[4] = {0, 0, 0, 0};
+    mutable std::vector<rc_texture> tex_views_;
     std::vector<rt::Material> materials_;
     std::vector<rt::Vertex> vertices_;
     std::vector<uint32_t> vtx_indices_;

@@ -80,6 +80,7 @@ rh_scene *rh_create_scene(rh_renderer *r) {
 }
 void rh_destroy_scene(rh_scene *s) { delete static_cast<SceneBase *>(S(s)); }
 void rh_set_environment(rh_scene *s, const rs_environment_desc *d) { S(s)->SetEnvironment(*d); }
+uint32_t rh_add_texture(rh_scene *s, const rs_tex_desc *d) { return S(s)->AddTexture(*d)._index; }
 uint32_t rh_add_material_node(rh_scene *s, const rs_shading_node_desc *d) { return S(s)->AddMaterial(*d)._index; }
 uint32_t rh_add_material_principled(rh_scene *s, const rs_principled_mat_desc *d) { return S(s)->AddMaterial(*d)._index; }
 uint32_t rh_add_mesh(rh_scene *s, const rs_mesh_desc *d) { return S(s)->AddMesh(*d)._index; }

@@ -36,6 +36,7 @@ enum : uint32_t { NODE_DIFFUSE = 0, NODE_GLOSSY, NODE_REFRACTIVE, NODE_EMISSIVE,
 
 constexpr int kTexNormals = 0, kTexBase = 1, kTexRough = 2, kTexMetallic = 3, kTexSpecular = 4;
 constexpr int kMixMat1 = 3, kMixMat2 = 4;
+constexpr uint32_t kTexSrgbBitHost = 1u << 24, kTexReconstructZBitHost = 2u << 24; // TEX_*_BIT, Core.h:159-160
 constexpr uint32_t kMatSolidBit = 32768, kMatIndexBits = 16383;
 constexpr uint32_t kMatFlagImpSample = 1u, kMatFlagMixAdd = 2u;
 constexpr float kMaxConeSpreadInc = 0.05f;

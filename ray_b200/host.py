@@ -22,7 +22,7 @@ FINAL, RAW, BASE_COLOR, DEPTH_NORMALS = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
     "rh_create_renderer", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
-    "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_add_material_node",
+    "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_add_texture", "rh_add_material_node",
     "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_add_light_directional",
     "rh_add_light_sphere", "rh_add_light_spot", "rh_add_light_rect", "rh_add_light_disk", "rh_add_light_line",
     "rh_add_camera", "rh_finalize", "rh_triangle_count", "rh_node_count", "rh_scene_view", "rh_get_camera", "rh_render",
@@ -54,6 +54,7 @@ def load_library():
         "rh_create_scene": (vp, [vp]),
         "rh_destroy_scene": (None, [vp]),
         "rh_set_environment": (None, [vp, P(capi.rs_environment_desc)]),
+        "rh_add_texture": (u32, [vp, P(capi.rs_tex_desc)]),
         "rh_add_material_node": (u32, [vp, P(capi.rs_shading_node_desc)]),
         "rh_add_material_principled": (u32, [vp, P(capi.rs_principled_mat_desc)]),
         "rh_add_mesh": (u32, [vp, P(capi.rs_mesh_desc)]),
@@ -132,6 +133,12 @@ class Scene:
         d = capi.rs_environment_desc(env_col=tuple(env_col), back_col=tuple(back_col),
                                      importance_sample=1 if importance_sample else 0)
         self.lib.rh_set_environment(self.h, C.byref(d))
+
+    def add_texture(self, pixels, is_srgb=True, is_normalmap=False, generate_mipmaps=False, reconstruct_z=False,
+                    convention=0):
+        """SceneBase::AddTexture for a (h, w, c) uint8 array, c in 1..4; returns the texture handle."""
+        d, keep = capi.make_tex_desc(pixels, is_srgb, is_normalmap, generate_mipmaps, reconstruct_z, convention)
+        return self.lib.rh_add_texture(self.h, C.byref(d))
 
     def add_material_node(self, d):
         return self.lib.rh_add_material_node(self.h, C.byref(d))

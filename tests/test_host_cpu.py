@@ -176,6 +176,39 @@ def test_lights_and_light_tree(built, oracle_mod):
     assert abs(mh - mo) / max(mo, 1e-6) < 0.06, (mh, mo)
 
 
+def _expanded_rgba(t):
+    """Level-0 texels of an rc_texture as (h, w, 4) with the channel expansion of TexStorage*::Fetch applied."""
+    w, h, n = int(t.res[0][0]), int(t.res[0][1]), int(t.channels)
+    a = np.ctypeslib.as_array(C.cast(t.pixels[0], C.POINTER(C.c_uint8)), shape=(h, w, n))
+    return np.concatenate([a] + [a[..., n - 1:n]] * (4 - n), axis=-1)
+
+
+def test_textures_and_textured_materials_match_reference(oracle_mod):
+    """SURVEY 8(f)-1 on the host side: AddTexture's storage choice / handle bits / normal-map repacking and the
+    material lowering with textures (alpha -> Mix with Transparent, emission -> additive Mix, triangle-light tex_index)
+    give the reference's material_t / light_t bytes and the reference's texels."""
+    desc = scenes.textured(32, 24)
+    hs = scenes.build(desc, host.Scene(None))
+    osc = scenes.build(desc, oracle_mod.Scene(wide=True))
+    assert host.load_library().rh_error_count(None) == 0, host.load_library().rh_last_error(None)
+    hv, ov = hs.view(), osc.view()
+    assert _arr(hv.materials, np.uint8).tobytes() == _arr(ov.materials, np.uint8).tobytes()
+    assert hv.texture_count == ov.texture_count == len(desc.textures)
+    href = {hv.textures[i].handle: hv.textures[i] for i in range(hv.texture_count)}
+    for i in range(ov.texture_count):
+        to = ov.textures[i]
+        th = href[to.handle]
+        assert [tuple(th.res[k]) for k in range(12)] == [tuple(to.res[k]) for k in range(12)]
+        assert np.array_equal(_expanded_rgba(th), _expanded_rgba(to)), hex(to.handle)
+    hl = _arr(hv.lights, np.uint32).reshape(-1, 16)
+    ol = _arr(ov.lights, np.uint32).reshape(-1, 16)
+    tri_h = sorted(int(x[6]) for x in hl if (x[0] & 7) == 5)  # light_t::tri.tex_index of LIGHT_TYPE_TRI lights
+    tri_o = sorted(int(x[6]) for x in ol if (x[0] & 7) == 5)
+    assert tri_h == tri_o and any(t != 0xffffffff for t in tri_h)
+    hs.close()
+    osc.close()
+
+
 def test_filter_tables_match_reference(oracle_mod):
     for filt, width in ((capi.FILTER_GAUSSIAN, 1.5), (capi.FILTER_BLACKMAN_HARRIS, 1.5), (capi.FILTER_BLACKMAN_HARRIS, 2.0)):
         desc = scenes.cornell_box(16, 16)

@@ -28,6 +28,7 @@ def _block_mean(img, b):
     ("hall_small", lambda: scenes.hall("principled", 128, 72, floor_res=32, n_columns=6, col_seg=10, col_rings=6,
                                        extra_lights=6), 192),
     ("instanced", lambda: scenes.instanced(25, 300, 96, 96), 128),
+    ("textured", lambda: scenes.textured(96, 72), 192),
 ])
 def test_host_layer_matches_reference_renderer(oracle_mod, name, make, spp):
     desc = make()
@@ -96,11 +97,14 @@ def test_regions_and_resize(oracle_mod):
 
 
 def test_unsupported_features_are_reported_not_faked():
+    """A material that names a texture the scene does not have must fail the upload, not render untextured."""
+    desc = scenes.cornell_box(16, 16)
+    desc.materials[0] = ("node", capi.rs_shading_node_desc.default(type=capi.NODE_DIFFUSE, base_color=(0.5, 0.5, 0.5)))
     r = host.Renderer(16, 16)
-    s = r.create_scene()
-    d = capi.rs_shading_node_desc.default(type=capi.NODE_DIFFUSE, base_texture=3)
-    s.add_material_node(d)
+    s = scenes.build(desc, r.create_scene())
+    s.add_material_node(capi.rs_shading_node_desc.default(type=capi.NODE_DIFFUSE, base_texture=(1 << 28) | 7))
     with pytest.raises(host.HostError):
+        r.render(s, (0, 0, 16, 16), 0, 1)
         r.check()
     s.close()
     r.close()
