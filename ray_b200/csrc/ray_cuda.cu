@@ -334,6 +334,19 @@ int harvest_stats(rc_ctx *ctx) {
     return 0;
 }
 
+// k_shade comes in a textured and an untextured build (all texture branches folded away); the scene decides.
+template <bool PRIMARY>
+void launch_shade(rc_ctx *ctx, int grid, cudaStream_t s, const KParams &p, RayBuf in, RayBuf out, int bounce, float limit0,
+                  float limit1, float mix_factor) {
+    if (ctx->tex_descs.count != 0) {
+        k_shade<PRIMARY, true><<<grid, RT_SHADE_THREADS, 0, s>>>(p, in, ctx->hits, out, ctx->shadow, bounce, limit0, limit1,
+                                                                  mix_factor);
+    } else {
+        k_shade<PRIMARY, false><<<grid, RT_SHADE_THREADS, 0, s>>>(p, in, ctx->hits, out, ctx->shadow, bounce, limit0,
+                                                                   limit1, mix_factor);
+    }
+}
+
 // Enqueue the kernels of one sample.
 int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     cudaStream_t s = ctx->stream;
@@ -376,8 +389,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     const float mix_factor = 1.0f / float(p.iteration);
     {
         const float lim = clamp_limit(p.ps.clamp_direct);
-        k_shade<true><<<shade_grid, RT_SHADE_THREADS, 0, s>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
-                                                  mix_factor);
+        launch_shade<true>(ctx, shade_grid, s, p, ctx->rays[0], ctx->rays[1], 0, lim, lim, mix_factor);
         ctx->kernel_launches[KF_SHADE]++;
     }
     record(ctx, EV_PSHADE);
@@ -411,9 +423,8 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
         record(ctx, e + 1);
         {
             const float cd = (bounce == 1) ? p.ps.clamp_direct : p.ps.clamp_indirect;
-            k_shade<false><<<shade_grid, RT_SHADE_THREADS, 0, s>>>(p, ctx->rays[cur], ctx->hits, ctx->rays[cur ^ 1], ctx->shadow,
-                                                       bounce, clamp_limit(cd), clamp_limit(p.ps.clamp_indirect),
-                                                       mix_factor);
+            launch_shade<false>(ctx, shade_grid, s, p, ctx->rays[cur], ctx->rays[cur ^ 1], bounce, clamp_limit(cd),
+                                clamp_limit(p.ps.clamp_indirect), mix_factor);
             ctx->kernel_launches[KF_SHADE]++;
         }
         record(ctx, e + 2);
@@ -622,8 +633,10 @@ int rc_create(int device, rc_ctx **out_ctx) {
     cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_trace_closest<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_trace_shadow, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_shade<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_shade<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_shade<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_shade<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     *out_ctx = ctx;
     return 0;
 }
@@ -1162,12 +1175,11 @@ int rc_stage_shade(rc_ctx *ctx, const rc_pass_desc *pass, int primary, int bounc
     const float mix_factor = 1.0f / float(p.iteration);
     if (primary) {
         const float lim = clamp_limit(p.ps.clamp_direct);
-        k_shade<true><<<grid, RT_SHADE_THREADS, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0, lim, lim,
-                                                      mix_factor);
+        launch_shade<true>(ctx, grid, ctx->stream, p, ctx->rays[0], ctx->rays[1], 0, lim, lim, mix_factor);
     } else {
         const float cd = (bounce == 1) ? p.ps.clamp_direct : p.ps.clamp_indirect;
-        k_shade<false><<<grid, RT_SHADE_THREADS, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, ctx->rays[1], ctx->shadow, 0,
-                                                       clamp_limit(cd), clamp_limit(p.ps.clamp_indirect), mix_factor);
+        launch_shade<false>(ctx, grid, ctx->stream, p, ctx->rays[0], ctx->rays[1], 0, clamp_limit(cd),
+                            clamp_limit(p.ps.clamp_indirect), mix_factor);
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaGetLastError());

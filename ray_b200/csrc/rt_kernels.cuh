@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_closest(KParams 
 
 // ---- ShadePrimary / ShadeSecondary (ShadeRef.cpp:1654-1737) --------------------------------------------------------
 // `bounce` = index of the ray list being shaded (0 = primary).  Secondary rays go to list bounce+1.
-template <bool PRIMARY>
+template <bool PRIMARY, bool TEX>
 __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS)
     k_shade(KParams p, RayBuf rays, HitBuf hits, RayBuf out_rays, ShadowBuf out_shadow, int bounce, float limit0,
             float limit1, float mix_factor) {
@@ -481,19 +481,19 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS)
             ray = load_ray(rays, i);
             inter = load_hit(hits, i);
             xy = ray.xy;
-            more = shade_surface_a(p.ps, limit0, inter, ray, p.rand_seed, p.iteration, p.sc, tl_stack, tl_factors, c, out);
+            more = shade_surface_a(TEX, p.ps, limit0, inter, ray, p.rand_seed, p.iteration, p.sc, tl_stack, tl_factors, c, out);
         }
 #if RT_SHADE_SYNC
         __syncthreads();
 #endif
         if (more) {
-            shade_surface_l(c);
+            shade_surface_l(TEX, c);
         }
 #if RT_SHADE_SYNC
         __syncthreads();
 #endif
         if (more) {
-            shade_surface_b(c, limit1, out);
+            shade_surface_b(TEX, c, limit1, out);
         }
         if (valid) {
             const int x = int((xy >> 16) & 0xffff), y = int(xy & 0xffff);

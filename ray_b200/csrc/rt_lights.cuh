@@ -390,7 +390,7 @@ struct SceneSurf { // the arrays shading needs besides SceneGeo
 
 // SampleLightSource with hierarchical NEE (USE_HIERARCHICAL_NEE, USE_SPHERICAL_AREA_LIGHT_SAMPLING = true).
 // Textured lights / env maps are not supported by this backend (rc_upload_scene rejects them).
-RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, const SceneGeo &sg, const SceneSurf &ss,
+RT_FN void sample_light_source(const bool tex_on, v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, const SceneGeo &sg, const SceneSurf &ss,
                                 const SceneTex &tx, float rand_pick_light, v2 rand_light_uv, v2 rand_tex_uv,
                                 LightSample &ls) {
     float u1 = rand_pick_light;
@@ -633,7 +633,7 @@ RT_FN void sample_light_source(v3 P, v3 T, v3 B, v3 N, const SceneLights &sl, co
         if (cos_theta > 0.0f) {
             ls.pdf = pdf;
             const uint32_t tex_index = __float_as_uint(l.p[2]); // light_t::tri.tex_index
-            if (tex_index != kTexInvalid) {
+            if (tex_on && tex_index != kTexInvalid) {
                 const c4 tex_color = tex_sample_color(tx, tex_index, luvs, 0, rand_tex_uv);
                 ls.col.x *= tex_color.x;
                 ls.col.y *= tex_color.y;

@@ -745,7 +745,7 @@ RT_FN void shade_node_emissive(MatCtx &c) {
     col += mix_weight * mis_weight * mat->tangent_rotation_or_strength * base_color;
 }
 
-RT_FN void shade_node_principled(MatCtx &c) {
+RT_FN void shade_node_principled(const bool tex_on, MatCtx &c) {
     const PassSettings &ps = *c.ps;
     const RayD &ray = *c.ray;
     const ShadeScene &sc = *c.sc;
@@ -773,12 +773,12 @@ RT_FN void shade_node_principled(MatCtx &c) {
     (void)rand_bsdf; (void)use_mis; (void)is_backfacing; (void)diff_d; (void)spec_d; (void)refr_d; (void)total_d;
     (void)tri_index; (void)tl_stack; (void)tl_factors;
     float metallic = unorm16(mat->metallic_unorm);
-    if (mat->textures[kTexMetallic] != kTexInvalid) { // ShadeRef.cpp:1540-1545 (no colour-space conversion)
+    if (tex_on && mat->textures[kTexMetallic] != kTexInvalid) { // ShadeRef.cpp:1540-1545 (no colour-space conversion)
         const uint32_t metallic_tex = mat->textures[kTexMetallic];
         metallic *= tex_unpack(tex_sample_bytes(sc.tex, metallic_tex, surf.uvs, tex_lod(sc.tex, metallic_tex, c.lambda), c.tex_rand)).x;
     }
     float specular = unorm16(mat->specular_unorm);
-    if (mat->textures[kTexSpecular] != kTexInvalid) { // ShadeRef.cpp:1547-1557
+    if (tex_on && mat->textures[kTexSpecular] != kTexInvalid) { // ShadeRef.cpp:1547-1557
         const uint32_t specular_tex = mat->textures[kTexSpecular];
         specular *= tex_sample_color(sc.tex, specular_tex, surf.uvs, tex_lod(sc.tex, specular_tex, c.lambda), c.tex_rand).x;
     }
@@ -976,9 +976,11 @@ RT_FN void shade_node_principled(MatCtx &c) {
 // them (RT_SHADE_SYNC):  a = miss / light hit / surface frame + mix resolution,  l = light sampling (NEE),
 // b = the material node + path continuation.  `c` carries everything from one phase to the next.
 // Phase a returns false when the ray is finished (out.col is final).
-RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &inter, const RayD &ray, uint32_t rand_seed,
-                            int iteration, const ShadeScene &sc, uint32_t *tl_stack, float *tl_factors, MatCtx &c,
-                            ShadeOut &out) {
+// `tex_on` is a compile-time constant at every call site (k_shade<PRIMARY, TEX>): untextured scenes run kernels from
+// which every texture branch has been folded away.
+RT_DEV bool shade_surface_a(const bool tex_on, const PassSettings &ps, float limit0, const Hit &inter, const RayD &ray,
+                            uint32_t rand_seed, int iteration, const ShadeScene &sc, uint32_t *tl_stack,
+                            float *tl_factors, MatCtx &c, ShadeOut &out) {
     out.has_secondary = out.has_shadow = false;
     out.wrote_aov = false;
     out.base_color = v3{0.0f, 0.0f, 0.0f};
@@ -1148,7 +1150,7 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     const float cone_width = ray.cone_width + ray.cone_spread * inter.t;
     // texture LOD term and jitter: only consumed by texture fetches (pure functions of the inputs, so skipping them for
     // untextured scenes changes nothing)
-    const bool has_tex = sc.tex.descs != nullptr;
+    const bool has_tex = tex_on;
     float lambda = 0.0f;
     v2 tex_rand = v2{0.0f, 0.0f};
     if (has_tex) {
@@ -1174,7 +1176,7 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     while (mat->type == NODE_MIX) {
         float mix_val = mat->tangent_rotation_or_strength;
         const uint32_t mix_texture = mat->textures[kTexBase];
-        if (mix_texture != kTexInvalid) {
+        if (tex_on && mix_texture != kTexInvalid) {
             mix_val *= tex_sample_color(sc.tex, mix_texture, surf.uvs, 0, tex_rand).x;
         }
         const float eta = is_backfacing ? safe_div_pos(ext_ior, mat->ior) : safe_div_pos(mat->ior, ext_ior);
@@ -1192,7 +1194,7 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     }
 
     // apply normal map (ShadeRef.cpp:1335-1349)
-    if (mat->textures[kTexNormals] != kTexInvalid) {
+    if (tex_on && mat->textures[kTexNormals] != kTexInvalid) {
         const uint32_t nh = mat->textures[kTexNormals];
         const c4 nc = tex_unpack(tex_sample_bytes(sc.tex, nh, surf.uvs, 0, tex_rand));
         const float nx = nc.x * 2.0f - 1.0f, ny = nc.y * 2.0f - 1.0f;
@@ -1269,7 +1271,7 @@ RT_DEV bool shade_surface_a(const PassSettings &ps, float limit0, const Hit &int
     return true;
 }
 
-RT_DEV void shade_surface_l(MatCtx &c) {
+RT_DEV void shade_surface_l(const bool tex_on, MatCtx &c) {
     const ShadeScene &sc = *c.sc;
     const Surface &surf = c.surf;
     LightSample &ls = c.ls;
@@ -1284,12 +1286,12 @@ RT_DEV void shade_surface_l(MatCtx &c) {
         const float rand_pick_light =
             rand2d(c.rand_dim + kRandDimLightPick, c.rand_hash, c.iteration - 1, sc.rand_seq).x;
         const v2 rand_light_uv = rand2d(c.rand_dim + kRandDimLight, c.rand_hash, c.iteration - 1, sc.rand_seq);
-        sample_light_source(surf.P, surf.T, surf.B, surf.N, sc.lights, sc.geo, sc.surf, sc.tex, rand_pick_light,
+        sample_light_source(tex_on, surf.P, surf.T, surf.B, surf.N, sc.lights, sc.geo, sc.surf, sc.tex, rand_pick_light,
                             rand_light_uv, c.tex_rand, ls);
     }
 }
 
-RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
+RT_DEV void shade_surface_b(const bool tex_on, MatCtx &c, float limit1, ShadeOut &out) {
     const PassSettings &ps = *c.ps;
     const RayD &ray = *c.ray;
     const ShadeScene &sc = *c.sc;
@@ -1305,7 +1307,7 @@ RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
     const float N_dot_L = dot(surf.N, ls.L);
 
     v3 base_color = mk3(mat->base_color);
-    if (mat->textures[kTexBase] != kTexInvalid) { // ShadeRef.cpp:1405-1419
+    if (tex_on && mat->textures[kTexBase] != kTexInvalid) { // ShadeRef.cpp:1405-1419
         const uint32_t base_texture = mat->textures[kTexBase];
         const c4 tex_color = tex_sample_color(sc.tex, base_texture, surf.uvs, tex_lod(sc.tex, base_texture, c.lambda), c.tex_rand);
         base_color.x *= tex_color.x;
@@ -1324,7 +1326,7 @@ RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
     }
 
     float roughness = unorm16(mat->roughness_unorm);
-    if (mat->textures[kTexRough] != kTexInvalid) { // ShadeRef.cpp:1440-1449
+    if (tex_on && mat->textures[kTexRough] != kTexInvalid) { // ShadeRef.cpp:1440-1449
         const uint32_t roughness_tex = mat->textures[kTexRough];
         roughness *= tex_sample_color(sc.tex, roughness_tex, surf.uvs, tex_lod(sc.tex, roughness_tex, c.lambda), c.tex_rand).x;
     }
@@ -1369,7 +1371,7 @@ RT_DEV void shade_surface_b(MatCtx &c, float limit1, ShadeOut &out) {
         case NODE_GLOSSY: shade_node_glossy(c); break;
         case NODE_REFRACTIVE: shade_node_refractive(c); break;
         case NODE_EMISSIVE: shade_node_emissive(c); break;
-        case NODE_PRINCIPLED: shade_node_principled(c); break;
+        case NODE_PRINCIPLED: shade_node_principled(tex_on, c); break;
         default: break;
         }
         col = c.col;
