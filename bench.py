@@ -327,15 +327,21 @@ def main():
         "wnodes", "mtris", "tri_indices", "tri_materials", "materials", "mesh_instances", "vertices", "vtx_indices",
         "lights", "light_cwnodes"))
     e2e_steps = max(min(a.steps, 8), 1)
+    if not use_dist:
+        r.pixels(host.RAW, copy=False)  # warm-up: the first read-back sets up the renderer's page-locked mirror
     r.reset_stats()
     if use_dist:
         torch.cuda.synchronize()
         tdist.barrier()
     t0 = time.perf_counter()
     host_frame = None
+    dbg = os.environ.get("BENCH_DEBUG")
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         r.invalidate_scene()
         it = r.render(s, rect, it, 1)
+        if dbg:
+            sys.stderr.write(f"[e2e] invalidate+render {1e3 * (time.perf_counter() - ta):.2f} ms\n")
         if use_dist:
             x, y, ww, hh = rect
             fr = rdist.gather_strips(frame_t[y:y + hh], w, H, dst=0)
@@ -345,7 +351,10 @@ def main():
                 host_frame.copy_(fr)
                 torch.cuda.synchronize()
         else:
-            img = r.pixels(host.RAW)
+            tb = time.perf_counter()
+            img = r.pixels(host.RAW, copy=False)  # borrowed view of the pinned mirror, as get_raw_pixels_ref()
+            if dbg:
+                sys.stderr.write(f"[e2e] pixels {1e3 * (time.perf_counter() - tb):.2f} ms\n")
     if use_dist:
         torch.cuda.synchronize()
         tdist.barrier()
@@ -371,8 +380,9 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes + 256),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "note": "per step: all scene arrays re-uploaded (pageable host memory), one blocking RenderScene, "
-                            "full frame read back into pinned memory"},
+                    "note": "per step: all scene arrays re-uploaded from the scene's page-locked host mirrors, one blocking "
+                            "RenderScene, full frame read back into the renderer's pinned mirror (borrowed, as "
+                            "get_raw_pixels_ref)"},
             "gpu_launches": launches_total, "clocks": clk,
             "rays": {"per_step": rays_total / a.steps, "shadow_per_step": shadow_total / a.steps,
                      "Mshadow_per_s": shadow_total / (ms * 1e-3) / 1e6},

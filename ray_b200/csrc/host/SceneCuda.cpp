@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // SceneCuda.cpp -- see SceneCuda.h.  Behavioural spec: reference internal/SceneCPU.cpp (file:line cited per function).
 #include "SceneCuda.h"
 
@@ -198,7 +199,43 @@ Scene::Scene(ILog *log) {
     log_ = log;
     SetEnvironment(environment_desc_t{{0, 0, 0}, {0, 0, 0}, 1});
 }
-Scene::~Scene() = default;
+Scene::~Scene() {
+    for (PinnedMirror &m : pinned_) {
+        rc_host_free(m.ptr);
+    }
+}
+
+void Scene::RefreshPinnedMirrors_nolock() {
+    if (getenv("RAY_HOST_NO_PINNED")) { // A/B switch for measurements
+        pinned_revision_ = 0;
+        return;
+    }
+    const void *src[PM_COUNT] = {wnodes_.data(),      mtris_.data(),       vertices_.data(),
+                                 vtx_indices_.data(), tri_indices_.data(), tri_materials_.data()};
+    const size_t bytes[PM_COUNT] = {wnodes_.size() * sizeof(rt::WNode),   mtris_.size() * sizeof(rt::MTri),
+                                    vertices_.size() * sizeof(rt::Vertex), vtx_indices_.size() * 4,
+                                    tri_indices_.size() * 4,               tri_materials_.size() * sizeof(rt::TriMat)};
+    bool ok = true;
+    for (int i = 0; i < PM_COUNT; ++i) {
+        PinnedMirror &m = pinned_[i];
+        if (bytes[i] > m.capacity) {
+            rc_host_free(m.ptr);
+            m.capacity = bytes[i] + bytes[i] / 8;
+            m.ptr = rc_host_alloc(m.capacity); // nullptr without a CUDA device: FillView then hands over the vectors
+            if (!m.ptr) {
+                m.capacity = 0;
+            }
+        }
+        m.bytes = 0;
+        if (m.ptr && bytes[i] != 0) {
+            memcpy(m.ptr, src[i], bytes[i]);
+            m.bytes = bytes[i];
+        } else if (bytes[i] != 0) {
+            ok = false;
+        }
+    }
+    pinned_revision_ = ok ? revision_ : 0;
+}
 
 void Scene::GetEnvironment(environment_desc_t &env) {
     std::shared_lock<std::shared_timed_mutex> lock(mtx_);
@@ -891,6 +928,7 @@ void Scene::Finalize(const ParallelFor &) {
     RebuildLightTree_nolock();
     GetBounds(bounds_min_, bounds_max_);
     ++revision_;
+    RefreshPinnedMirrors_nolock();
 }
 
 // reference SceneCPU.cpp:928-1015
@@ -1264,6 +1302,14 @@ void Scene::FillView(rc_scene_view &v) const {
     v.sky_map_spread_angle = 0.0f;
     memcpy(v.bounds_min, bounds_min_, sizeof(v.bounds_min));
     memcpy(v.bounds_max, bounds_max_, sizeof(v.bounds_max));
+    if (pinned_revision_ == revision_) { // same bytes, page-locked
+        const rc_array *dst[PM_COUNT] = {&v.wnodes, &v.mtris, &v.vertices, &v.vtx_indices, &v.tri_indices, &v.tri_materials};
+        for (int i = 0; i < PM_COUNT; ++i) {
+            if (pinned_[i].bytes == size_t(dst[i]->count) * dst[i]->stride && pinned_[i].bytes != 0) {
+                const_cast<rc_array *>(dst[i])->ptr = pinned_[i].ptr;
+            }
+        }
+    }
     tex_views_.clear();
     for (const TexImage &img : textures_) {
         rc_texture t = {};

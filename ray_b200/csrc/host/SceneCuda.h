@@ -38,6 +38,16 @@ class Scene final : public SceneBase {
     std::vector<TexImage> textures_;
     uint32_t tex_storage_counts_[4] = {0, 0, 0, 0};
     mutable std::vector<rc_texture> tex_views_;
+    // Page-locked copies of the big geometry arrays, refreshed by Finalize: FillView hands these to rc_upload_scene so a
+    // (re-)upload is a straight DMA at PCIe speed instead of the driver staging pageable vectors through a bounce buffer.
+    struct PinnedMirror {
+        void *ptr = nullptr;
+        size_t capacity = 0, bytes = 0;
+    };
+    enum { PM_WNODES = 0, PM_MTRIS, PM_VERTICES, PM_VTX_INDICES, PM_TRI_INDICES, PM_TRI_MATERIALS, PM_COUNT };
+    PinnedMirror pinned_[PM_COUNT];
+    uint64_t pinned_revision_ = 0;
+    void RefreshPinnedMirrors_nolock();
     std::vector<rt::Material> materials_;
     std::vector<rt::Vertex> vertices_;
     std::vector<uint32_t> vtx_indices_;

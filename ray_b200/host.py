@@ -252,11 +252,15 @@ class Renderer:
         self.check()
         return it.value
 
-    def pixels(self, which=RAW):
+    def pixels(self, which=RAW, copy=True):
+        """RendererBase::get_pixels_ref / get_raw_pixels_ref / get_aux_pixels_ref: reads the plane back into the
+        renderer's page-locked mirror.  copy=False returns a view of that mirror, BORROWED exactly like the reference's
+        color_data_rgba_t (valid until the next RenderScene / Resize); copy=True detaches it."""
         pitch = C.c_int(0)
         p = self.lib.rh_get_pixels(self.h, which, C.byref(pitch))
         self.check()
-        return np.ctypeslib.as_array(p, shape=(self.hh, pitch.value, 4))[:, :self.w, :].copy()
+        a = np.ctypeslib.as_array(p, shape=(self.hh, pitch.value, 4))[:, :self.w, :]
+        return a.copy() if copy else a
 
     def stats_us(self):
         a = (C.c_uint64 * 11)()
