@@ -147,3 +147,35 @@ def test_full_render_matches_reference_renderer(pair, oracle_mod, sort):
     assert np.abs(final - ref_final).max() <= 2e-6
     c = pair.ctx.counters()
     assert c["primary_rays"] >= spp * pair.w * pair.h
+    if sort:
+        # AOVs (running means of base colour and depth / normals, ShadeRef.cpp:1677-1698); the stage test above left
+        # them dirty, so compare a run that starts from zeroed planes
+        pair.ctx.resize(pair.w + 1, pair.h)
+        pair.ctx.resize(pair.w, pair.h)
+        for i in range(1, spp + 1):
+            pair.ctx.render(pair.make_pass(i, flags=flags))
+        assert bits_equal(pair.ctx.readback(capi.RC_BUF_BASE_COLOR), ref_base), "base colour AOV"
+        assert bits_equal(pair.ctx.readback(capi.RC_BUF_DEPTH_NORMALS), ref_dn), "depth-normals AOV"
+
+
+def test_adaptive_sampling_matches_reference_renderer(oracle_mod):
+    """variance estimate + required_samples (RendererCPU.h:607-658): pixels whose two half-buffers agree stop being
+    sampled after min_samples, raygen skips them (CoreRef.cpp:1446-1449).  Same image, bit for bit, as RendererRef."""
+    desc = scenes.cornell_box(64, 64)
+    desc.camera.min_samples = 4
+    desc.camera.variance_threshold = 0.02
+    pair = Pair(oracle_mod, desc)
+    spp = 12
+    ref = oracle_mod.Renderer(capi.RT_REFERENCE, pair.w, pair.h)
+    it = 0
+    for _ in range(spp):
+        it = ref.render(pair.osc, (0, 0, pair.w, pair.h), it)
+    ref_raw = ref.pixels(1)
+    ref.close()
+    pair.ctx.clear((0, 0, 0, 0))
+    for i in range(1, spp + 1):
+        pair.ctx.render(pair.make_pass(i))
+    assert bits_equal(pair.ctx.readback(capi.RC_BUF_RAW), ref_raw)
+    c = pair.ctx.counters()
+    assert c["primary_rays"] < spp * pair.w * pair.h, "no pixel converged: the adaptive path was not exercised"
+    pair.close()
