@@ -74,18 +74,23 @@ typedef struct rc_scene_view {
     uint32_t visible_lights_count, blocker_lights_count;
     /* environment_t subset (Core.h:393-410) */
     float env_col[3];
-    uint32_t env_map;        /* must be 0xffffffff: env maps are out of scope */
+    uint32_t env_map;        /* 0xffffffff or the handle of an RGBE lat-long texture of the RGBA storage (in `textures`) */
     float back_col[3];
-    uint32_t back_map;       /* must be 0xffffffff */
+    uint32_t back_map;       /* likewise, for camera rays */
     uint32_t env_light_index;
-    float sky_map_spread_angle; /* must be 0 */
+    float sky_map_spread_angle; /* must be 0: the procedural sky is out of scope */
     /* Cpu::Scene::GetBounds (ray-sort grid) */
     float bounds_min[3], bounds_max[3];
     /* textures referenced by materials / triangle lights (NULL / 0 for an untextured scene).  YCoCg-coded textures
      * (TEX_YCOCG_BIT, only produced with texture compression on) are rejected. */
     const rc_texture *textures;
     uint32_t texture_count;
-    uint32_t _pad0;
+    /* environment map sampling (environment_t, Core.h:393-410): rotations in radians and the importance-sampling
+     * quad-tree built by Cpu::Scene::PrepareEnvMapQTree_nolock (SceneCPU.cpp:1058-1211): level i is an array of
+     * 4^(qtree_levels-1-i) fvec4 (four quadrant luminances each), exactly environment_t::qtree_mips[i] */
+    int32_t qtree_levels;
+    float env_map_rotation, back_map_rotation;
+    const float *qtree_mips[16];
 } rc_scene_view;
 
 /* camera_t (reference Types.h:102-115) + pass_settings_t (Types.h:92-100), flattened to 32-bit fields. */

@@ -10,7 +10,7 @@
  *   rs_mesh_instance_desc   <- Ray::mesh_instance_desc_t     (SceneBase.h:134-142)
  *   rs_*_light_desc         <- Ray::{directional,sphere,spot,rect,disk,line}_light_desc_t (SceneBase.h:200-268)
  *   rs_camera_desc          <- Ray::camera_desc_t            (SceneBase.h:271-311)
- *   rs_environment_desc     <- Ray::environment_desc_t       (SceneBase.h:347-357), constant-colour subset
+ *   rs_environment_desc     <- Ray::environment_desc_t       (SceneBase.h:347-357) without the procedural sky
  *
  * Field names, meaning and defaults are the reference's. Handles are the 32-bit `_index` of the reference's
  * {_index,_block} handle pairs; RS_INVALID (0xffffffff) is "no handle".
@@ -202,6 +202,10 @@ typedef struct rs_environment_desc {
     float env_col[3];
     float back_col[3];
     uint32_t importance_sample; /* bool */
+    uint32_t env_map;           /* RS_INVALID or the handle of an RGBA8888 texture holding RGBE (lat-long) */
+    uint32_t back_map;          /* likewise, seen by camera rays */
+    float env_map_rotation;     /* radians */
+    float back_map_rotation;
 } rs_environment_desc;
 
 /* Fill a descriptor with the reference's defaults (SceneBase.h initialisers). */

@@ -108,6 +108,12 @@ class OracleScene final : public Cpu::Scene {
         v.sky_map_spread_angle = env_.sky_map_spread_angle;
         GetBounds(v.bounds_min, v.bounds_max);
         export_textures(v);
+        v.env_map_rotation = env_.env_map_rotation;
+        v.back_map_rotation = env_.back_map_rotation;
+        v.qtree_levels = env_.qtree_levels;
+        for (int i = 0; i < 16; ++i) {
+            v.qtree_mips[i] = (i < env_.qtree_levels) ? env_.qtree_mips[i] : nullptr;
+        }
     }
 
     const camera_t &cam() const { return cams_[current_cam_._index]; }
@@ -444,6 +450,10 @@ void ro_set_environment(ro_scene *s, const rs_environment_desc *d) {
     memcpy(e.env_col, d->env_col, sizeof(e.env_col));
     memcpy(e.back_col, d->back_col, sizeof(e.back_col));
     e.importance_sample = d->importance_sample != 0;
+    e.env_map = th(d->env_map);
+    e.back_map = th(d->back_map);
+    e.env_map_rotation = d->env_map_rotation;
+    e.back_map_rotation = d->back_map_rotation;
     reinterpret_cast<OracleScene *>(s)->SetEnvironment(e);
 }
 

@@ -151,7 +151,8 @@ class rs_camera_desc(C.Structure):
 
 
 class rs_environment_desc(C.Structure):
-    _fields_ = [("env_col", f32 * 3), ("back_col", f32 * 3), ("importance_sample", u32)]
+    _fields_ = [("env_col", f32 * 3), ("back_col", f32 * 3), ("importance_sample", u32), ("env_map", u32),
+                ("back_map", u32), ("env_map_rotation", f32), ("back_map_rotation", f32)]
 
 
 # ---- include/ray_cuda.h -------------------------------------------------------------------------------------------
@@ -174,7 +175,8 @@ class rc_scene_view(C.Structure):
                 ("tlas_root", u32), ("visible_lights_count", u32), ("blocker_lights_count", u32),
                 ("env_col", f32 * 3), ("env_map", u32), ("back_col", f32 * 3), ("back_map", u32),
                 ("env_light_index", u32), ("sky_map_spread_angle", f32), ("bounds_min", f32 * 3),
-                ("bounds_max", f32 * 3), ("textures", C.POINTER(rc_texture)), ("texture_count", u32), ("_pad0", u32)]
+                ("bounds_max", f32 * 3), ("textures", C.POINTER(rc_texture)), ("texture_count", u32), ("qtree_levels", i32),
+                ("env_map_rotation", f32), ("back_map_rotation", f32), ("qtree_mips", C.c_void_p * 16)]
 
 
 class rc_camera(C.Structure):

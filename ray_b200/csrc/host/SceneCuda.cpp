@@ -197,7 +197,7 @@ void InverseMatrix4(const float m[16], float out[16]) {
 
 Scene::Scene(ILog *log) {
     log_ = log;
-    SetEnvironment(environment_desc_t{{0, 0, 0}, {0, 0, 0}, 1});
+    SetEnvironment(environment_desc_t{{0, 0, 0}, {0, 0, 0}, 1, RS_INVALID, RS_INVALID, 0.0f, 0.0f});
 }
 Scene::~Scene() {
     for (PinnedMirror &m : pinned_) {
@@ -916,7 +916,11 @@ void Scene::Finalize(const ParallelFor &) {
         light_alive_[env_light_index_] = 0;
         env_light_index_ = 0xffffffffu;
     }
+    env_qtree_mips_.clear();
     if (env_.importance_sample && env_.env_col[0] > 0.0f && env_.env_col[1] > 0.0f && env_.env_col[2] > 0.0f) {
+        if (env_.env_map != RS_INVALID) {
+            PrepareEnvMapQTree_nolock();
+        }
         rt::Light l;
         memset(&l, 0, sizeof(l));
         l.bits = light_bits(rt::LIGHT_ENV, false, true, true, false,
@@ -929,6 +933,145 @@ void Scene::Finalize(const ParallelFor &) {
     GetBounds(bounds_min_, bounds_max_);
     ++revision_;
     RefreshPinnedMirrors_nolock();
+}
+
+const Scene::TexImage *Scene::FindTexture(uint32_t handle) const {
+    for (const TexImage &t : textures_) {
+        if (t.handle == (handle & 0xf0ffffffu)) {
+            return &t;
+        }
+    }
+    return nullptr;
+}
+
+namespace {
+// Core.cpp:110-128 / Core.h:410-417 / CoreRef.h:234-237 on the host (same libm as the reference)
+void canonical_to_dir(const float p[2], float y_rotation, float out_d[3]) {
+    const float cos_theta = 2 * p[0] - 1;
+    float phi = 2 * PI * p[1] + y_rotation;
+    if (phi < 0) {
+        phi += 2 * PI;
+    }
+    if (phi > 2 * PI) {
+        phi -= 2 * PI;
+    }
+    const float sin_theta = sqrtf(1 - cos_theta * cos_theta);
+    const float sin_phi = sinf(phi);
+    const float cos_phi = cosf(phi);
+    out_d[0] = sin_theta * cos_phi;
+    out_d[1] = cos_theta;
+    out_d[2] = -sin_theta * sin_phi;
+}
+float to_norm_float(uint8_t v) {
+    const uint32_t val = 0x3f800000u + v * 0x8080u + (v + 1u) / 2u;
+    float f;
+    memcpy(&f, &val, 4);
+    return f - 1.0f;
+}
+float fractf_(float v) { return v - floorf(v); }
+} // namespace
+
+// reference SceneCPU.cpp:1058-1211
+void Scene::PrepareEnvMapQTree_nolock() {
+    const TexImage *img = FindTexture(env_.env_map);
+    if (!img || img->channels != 4) {
+        log_->Error("Ray(CUDA): the environment map must be an RGBA8888 (RGBE) texture of this scene");
+        return;
+    }
+    const int size[2] = {img->w, img->h};
+    const int lowest_dim = std::min(size[0], size[1]);
+    int res = 1;
+    while (2 * res < lowest_dim) {
+        res *= 2;
+    }
+    int cur_res = res;
+    float total_lum = 0.0f;
+    std::vector<std::vector<float>> mips;
+    { // the first quad-tree level: 5x5 Gaussian footprint around every cell centre, looked up through the lat-long mapping
+        mips.emplace_back(size_t(cur_res) * cur_res / 4 * 4, 0.0f);
+        static const float FilterWeights[][5] = {{1 / 273.0f, 4 / 273.0f, 7 / 273.0f, 4 / 273.0f, 1 / 273.0f},
+                                                 {4 / 273.0f, 16 / 273.0f, 26 / 273.0f, 16 / 273.0f, 4 / 273.0f},
+                                                 {7 / 273.0f, 26 / 273.0f, 41 / 273.0f, 26 / 273.0f, 7 / 273.0f},
+                                                 {4 / 273.0f, 16 / 273.0f, 26 / 273.0f, 16 / 273.0f, 4 / 273.0f},
+                                                 {1 / 273.0f, 4 / 273.0f, 7 / 273.0f, 4 / 273.0f, 1 / 273.0f}};
+        static const float FilterSize = 0.5f;
+        for (int qy = 0; qy < cur_res; ++qy) {
+            for (int qx = 0; qx < cur_res; ++qx) {
+                for (int jj = -2; jj <= 2; ++jj) {
+                    for (int ii = -2; ii <= 2; ++ii) {
+                        const float q[2] = {fractf_(1.0f + (float(qx) + 0.5f + ii * FilterSize) / cur_res),
+                                            fractf_(1.0f + (float(qy) + 0.5f + jj * FilterSize) / cur_res)};
+                        float dir[3];
+                        canonical_to_dir(q, 0.0f, dir);
+                        const float theta = acosf(std::min(std::max(dir[1], -1.0f), 1.0f)) / PI;
+                        float phi = atan2f(dir[2], dir[0]);
+                        if (phi < 0) {
+                            phi += 2 * PI;
+                        }
+                        if (phi > 2 * PI) {
+                            phi -= 2 * PI;
+                        }
+                        const float u = fractf_(0.5f * phi / PI);
+                        const float uvs[2] = {u * float(size[0]), theta * float(size[1])};
+                        const int ix = std::min(std::max(int(uvs[0]), 0), size[0] - 1);
+                        const int iy = std::min(std::max(int(uvs[1]), 0), size[1] - 1);
+                        const uint8_t *px = &img->pixels[(size_t(iy) * size[0] + ix) * 4];
+                        const float f = exp2f(float(px[3]) - 128.0f);
+                        const float cur_lum = (to_norm_float(px[0]) * f + to_norm_float(px[1]) * f + to_norm_float(px[2]) * f);
+                        const int index = (qx & 1) | ((qy & 1) << 1);
+                        float &qv = mips[0][(size_t(qy / 2) * cur_res / 2 + (qx / 2)) * 4 + index];
+                        qv = qv + cur_lum * FilterWeights[ii + 2][jj + 2];
+                    }
+                }
+            }
+        }
+        for (size_t i = 0; i < mips[0].size(); i += 4) {
+            const float *v = &mips[0][i];
+            total_lum += ((v[0] + v[1]) + v[2]) + v[3]; // fvec4::hsum (SSE2 build of the reference)
+        }
+        cur_res /= 2;
+    }
+    while (cur_res > 1) {
+        mips.emplace_back(size_t(cur_res) * cur_res / 4 * 4, 0.0f);
+        const std::vector<float> &prev = mips[mips.size() - 2];
+        for (int y = 0; y < cur_res; ++y) {
+            for (int x = 0; x < cur_res; ++x) {
+                const float *pv = &prev[(size_t(y) * cur_res + x) * 4];
+                const float res_lum = pv[0] + pv[1] + pv[2] + pv[3];
+                const int index = (x & 1) | ((y & 1) << 1);
+                mips.back()[(size_t(y / 2) * cur_res / 2 + (x / 2)) * 4 + index] = res_lum;
+            }
+        }
+        cur_res /= 2;
+    }
+    // how many levels are actually required
+    static const float LumFractThreshold = 0.005f;
+    cur_res = 2;
+    int the_last_required_lod = 0;
+    for (int lod = int(mips.size()) - 1; lod >= 0; --lod) {
+        the_last_required_lod = lod;
+        const std::vector<float> &cur = mips[lod];
+        bool subdivision_required = false;
+        for (int y = 0; y < (cur_res / 2) && !subdivision_required; ++y) {
+            for (int x = 0; x < (cur_res / 2) && !subdivision_required; ++x) {
+                const float *v = &cur[(size_t(y) * cur_res / 2 + x) * 4];
+                const float thr = LumFractThreshold * total_lum;
+                subdivision_required |= (v[0] > thr) || (v[1] > thr) || (v[2] > thr) || (v[3] > thr);
+            }
+        }
+        if (!subdivision_required) {
+            break;
+        }
+        cur_res *= 2;
+    }
+    if (the_last_required_lod > 0) {
+        mips.erase(mips.begin(), mips.begin() + the_last_required_lod);
+    }
+    if (mips.size() > 16) {
+        log_->Error("Ray(CUDA): environment quad-tree deeper than 16 levels");
+        return;
+    }
+    env_qtree_mips_ = std::move(mips);
 }
 
 // reference SceneCPU.cpp:928-1015
@@ -1295,9 +1438,15 @@ void Scene::FillView(rc_scene_view &v) const {
     v.visible_lights_count = visible_lights_count_;
     v.blocker_lights_count = blocker_lights_count_;
     memcpy(v.env_col, env_.env_col, sizeof(v.env_col));
-    v.env_map = 0xffffffffu;
+    v.env_map = env_.env_map;
     memcpy(v.back_col, env_.back_col, sizeof(v.back_col));
-    v.back_map = 0xffffffffu;
+    v.back_map = env_.back_map;
+    v.env_map_rotation = env_.env_map_rotation;
+    v.back_map_rotation = env_.back_map_rotation;
+    v.qtree_levels = int(env_qtree_mips_.size());
+    for (int i = 0; i < v.qtree_levels; ++i) {
+        v.qtree_mips[i] = env_qtree_mips_[i].data();
+    }
     v.env_light_index = env_light_index_;
     v.sky_map_spread_angle = 0.0f;
     memcpy(v.bounds_min, bounds_min_, sizeof(v.bounds_min));

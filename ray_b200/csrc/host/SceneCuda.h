@@ -48,6 +48,10 @@ class Scene final : public SceneBase {
     PinnedMirror pinned_[PM_COUNT];
     uint64_t pinned_revision_ = 0;
     void RefreshPinnedMirrors_nolock();
+    // importance-sampling quad-tree of the environment map (reference env_map_qtree_, SceneCPU.h / SceneCPU.cpp:1058-1211)
+    std::vector<std::vector<float>> env_qtree_mips_; // level i: 4^(levels-1-i) quads x 4 floats
+    void PrepareEnvMapQTree_nolock();
+    const TexImage *FindTexture(uint32_t handle) const;
     std::vector<rt::Material> materials_;
     std::vector<rt::Vertex> vertices_;
     std::vector<uint32_t> vtx_indices_;

@@ -61,7 +61,8 @@ struct rc_ctx {
 
     DevArray wnodes, mtris, tri_indices, tri_materials, materials, mesh_instances, vertices, vtx_indices, lights,
         light_cwnodes;
-    DevArray tex_descs, tex_texels;
+    DevArray tex_descs, tex_texels, qtree;
+    SceneEnv env{};
     float *d_srgb_lut = nullptr;
     bool have_scene = false;
     rc_scene_view scene_info{};
@@ -221,6 +222,8 @@ int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     p.sc.tex.descs = ctx->tex_descs.count ? static_cast<const TexDesc *>(ctx->tex_descs.ptr) : nullptr;
     p.sc.tex.texels = static_cast<const uint32_t *>(ctx->tex_texels.ptr);
     p.sc.tex.srgb_lut = ctx->d_srgb_lut;
+    p.sc.lights.env = ctx->env;
+    p.sc.lights.env.qtree = static_cast<const float4 *>(ctx->qtree.ptr);
     p.sc.lights.lights = static_cast<const Light *>(ctx->lights.ptr);
     p.sc.lights.nodes = static_cast<const LightCWNode *>(ctx->light_cwnodes.ptr);
     p.sc.lights.nodes_count = ctx->light_cwnodes.count;
@@ -678,7 +681,7 @@ void rc_destroy(rc_ctx *ctx) {
     cudaFree(ctx->d_srgb_lut);
     for (DevArray *a : {&ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
-                        &ctx->tex_descs, &ctx->tex_texels}) {
+                        &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {
         cudaFree(a->ptr);
     }
     if (ctx->stream) {
@@ -799,9 +802,6 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
         return fail(ctx, "rc_upload_scene: null argument");
     }
     cudaSetDevice(ctx->device);
-    if (sv->env_map != 0xffffffffu || sv->back_map != 0xffffffffu) {
-        return fail(ctx, "rc_upload_scene: environment maps are not supported by the CUDA backend");
-    }
     if (sv->sky_map_spread_angle != 0.0f) {
         return fail(ctx, "rc_upload_scene: procedural sky is not supported by the CUDA backend");
     }
@@ -914,6 +914,34 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
             memcpy(&lts[i].p[2], &h, 4);
         }
     }
+    // environment: map handles -> dense ids, quad-tree levels concatenated
+    SceneEnv env{};
+    env.env_map = sv->env_map;
+    env.back_map = sv->back_map;
+    if (patch(env.env_map, "environment map", 0, 0) || patch(env.back_map, "background map", 0, 0)) {
+        return 1;
+    }
+    if (env.env_map != 0xffffffffu) {
+        env.env_map &= kTexIdBits;
+    }
+    if (env.back_map != 0xffffffffu) {
+        env.back_map &= kTexIdBits;
+    }
+    env.env_map_rotation = sv->env_map_rotation;
+    env.back_map_rotation = sv->back_map_rotation;
+    env.qtree_levels = sv->qtree_levels;
+    std::vector<float> qtree;
+    if (sv->qtree_levels < 0 || sv->qtree_levels > kMaxQTreeLevels) {
+        return fail(ctx, "rc_upload_scene: qtree_levels %d out of range", sv->qtree_levels);
+    }
+    for (int i = 0; i < sv->qtree_levels; ++i) {
+        if (!sv->qtree_mips[i]) {
+            return fail(ctx, "rc_upload_scene: quad-tree level %d is null", i);
+        }
+        const size_t quads = size_t(1) << (2 * (sv->qtree_levels - 1 - i));
+        env.qtree_offset[i] = uint32_t(qtree.size() / 4);
+        qtree.insert(qtree.end(), sv->qtree_mips[i], sv->qtree_mips[i] + quads * 4);
+    }
     rc_scene_view patched = *sv;
     patched.materials.ptr = mats.data();
     patched.lights.ptr = lts.data();
@@ -934,16 +962,21 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
     {
         const rc_array da{descs.data(), uint32_t(descs.size()), uint32_t(sizeof(TexDesc))};
         const rc_array ta{texels.data(), uint32_t(texels.size()), 4u};
+        const rc_array qa{qtree.data(), uint32_t(qtree.size() / 4), 16u};
         if (upload_array(ctx, ctx->tex_descs, da, sizeof(TexDesc), "texture descriptors") ||
-            upload_array(ctx, ctx->tex_texels, ta, 4, "texels")) {
+            upload_array(ctx, ctx->tex_texels, ta, 4, "texels") || upload_array(ctx, ctx->qtree, qa, 16, "env quad-tree")) {
             return 1;
         }
+        ctx->env = env;
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // descs / texels / mats / lts are locals
     }
     ctx->scene_info = *sv;
     ctx->scene_info.materials.ptr = nullptr;
     ctx->scene_info.lights.ptr = nullptr;
     ctx->scene_info.textures = nullptr;
+    for (const float *&q : ctx->scene_info.qtree_mips) {
+        q = nullptr;
+    }
     ctx->li_count = sv->li_indices.count;
     set_sort_bounds(ctx->sort, sv->bounds_min, sv->bounds_max);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

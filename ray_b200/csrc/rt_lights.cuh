@@ -9,7 +9,7 @@
 //   IntersectAreaLights(shadow, cwbvh) :4451-4592             EvalTriLightFactor(cwbvh)          :4692-4736
 #pragma once
 
-#include "rt_tex.cuh"
+#include "rt_env.cuh"
 #include "rt_traverse.cuh"
 
 namespace rt {
@@ -36,6 +36,7 @@ struct SceneLights {
     uint32_t visible_lights_count, blocker_lights_count;
     uint32_t env_light_index;
     float env_col[3], back_col[3];
+    SceneEnv env;
 };
 
 // Unpack the 8 quantised child boxes of a light-tree node into [3][8] arrays.
@@ -528,7 +529,11 @@ RT_FN void sample_light_source(const bool tex_on, v3 P, v3 T, v3 B, v3 N, const 
             ls.pdf = (pdf > 0.0f) ? pdf : (ls_dist * ls_dist) / (rect_area * cos_theta);
             ls.area = l_visible(l) ? rect_area : 0.0f;
             if (l_sky_portal(l)) {
-                ls.col *= mk3(sl.env_col);
+                v3 env_col = mk3(sl.env_col);
+                if (tex_on && sl.env.env_map != kTexInvalid) {
+                    env_col *= sample_latlong_rgbe(tx, sl.env.env_map, ls.L, sl.env.env_map_rotation, rand_tex_uv);
+                }
+                ls.col *= env_col;
                 ls.from_env = true;
             }
         }
@@ -564,7 +569,11 @@ RT_FN void sample_light_source(const bool tex_on, v3 P, v3 T, v3 B, v3 N, const 
             ls.area = 0.0f;
         }
         if (l_sky_portal(l)) {
-            ls.col *= mk3(sl.env_col);
+            v3 env_col = mk3(sl.env_col);
+            if (tex_on && sl.env.env_map != kTexInvalid) {
+                env_col *= sample_latlong_rgbe(tx, sl.env.env_map, ls.L, sl.env.env_map_rotation, rand_tex_uv);
+            }
+            ls.col *= env_col;
             ls.from_env = true;
         }
     } else if (type == LIGHT_LINE) {
@@ -641,19 +650,29 @@ RT_FN void sample_light_source(const bool tex_on, v3 P, v3 T, v3 B, v3 N, const 
             }
         }
     } else if (type == LIGHT_ENV) {
-        // no env map => no quad-tree (SceneCPU.cpp:905-908): sample the hemisphere around N
         const float rx = rand_light_uv.x, ry = rand_light_uv.y;
-        const float phi = 2 * kPi * ry;
-        const v2 sc = portable_sincos(phi);
-        const float cos_phi = sc.y, sin_phi = sc.x;
-        const float dir = sqrtf(1.0f - rx * rx);
-        const v3 V = v3{dir * cos_phi, dir * sin_phi, rx};
-        ls.L = world_from_tangent(T, B, N, V);
+        float env_pdf;
+        if (tex_on && sl.env.qtree_levels != 0) {
+            // importance-sample the environment map through its quad-tree (CoreRef.cpp:3579-3584)
+            ls.L = sample_env_qtree(sl.env, sl.env.env_map_rotation, u1, rx, ry, &env_pdf);
+        } else {
+            // no quad-tree (no env map, SceneCPU.cpp:905-908): sample the hemisphere around N
+            const float phi = 2 * kPi * ry;
+            const v2 sc = portable_sincos(phi);
+            const float cos_phi = sc.y, sin_phi = sc.x;
+            const float dir = sqrtf(1.0f - rx * rx);
+            const v3 V = v3{dir * cos_phi, dir * sin_phi, rx};
+            ls.L = world_from_tangent(T, B, N, V);
+            env_pdf = 0.5f / kPi;
+        }
         ls.col *= mk3(sl.env_col);
+        if (tex_on && sl.env.env_map != kTexInvalid) {
+            ls.col *= sample_latlong_rgbe(tx, sl.env.env_map, ls.L, sl.env.env_map_rotation, rand_tex_uv);
+        }
         ls.area = 1.0f;
         ls.lp = P + ls.L;
         ls.dist_mul = kMaxDist;
-        ls.pdf = 0.5f / kPi;
+        ls.pdf = env_pdf;
         ls.from_env = true;
         ls.ray_flags = l_ray_visibility(l);
     }

@@ -261,6 +261,165 @@ RT_FN float libm_acosf(float x) {
     }
 }
 
+// sinf / cosf / atan2f of the host libm (glibc 2.39), restated.  The environment-map code of the reference calls them
+// (SampleLatlong_RGBE CoreRef.cpp:2995-3039, CanonicalToDir / DirToCanonical Core.cpp:110-143) and the results index
+// texels / quad-tree cells, so one ulp matters.  sinf/cosf: glibc's sysdeps/ieee754/flt-32/s_sincosf.h (the Arm
+// optimized-routines algorithm: double-precision polynomial after a fast reduction by pi/2; arguments here are angles in
+// [-7, 7], far below the 120.0f where the big-argument reduction starts).  atan2f/atanf: the fdlibm float versions
+// (e_atan2f.c, s_atanf.c).  tests/test_libm.py compares all of them bit for bit with the host libm.
+RT_FN float libm_sincosf_poly(double x, double x2, bool second_table, int n) {
+    // __sincosf_table[0] / [1]: the second table negates the cosine coefficients
+    const double sg = second_table ? -1.0 : 1.0;
+    const double c0 = sg * 0x1p0, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5,
+                 c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0) {
+        const double x3 = x * x2;
+        const double t1 = s2 + x2 * s3;
+        const double x7 = x3 * x2;
+        const double s = x + x3 * s1;
+        return float(s + x7 * t1);
+    } else {
+        const double x4 = x2 * x2;
+        const double t2 = c3 + x2 * c4;
+        const double t1 = c0 + x2 * c1;
+        const double x6 = x4 * x2;
+        const double c = t1 + x4 * c2;
+        return float(c + x6 * t2);
+    }
+}
+
+RT_FN float libm_sinf(float y) {
+    double x = double(y);
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+    if (top < 0x3f4u) { // |y| < pi/4
+        if (top < 0x398u) { // |y| < 2^-12
+            return y;
+        }
+        return libm_sincosf_poly(x, x * x, false, 0);
+    }
+    const double r = x * 0x1.45F306DC9C883p+23;
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = x - double(n) * 0x1.921FB54442D18p0;
+    const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    return libm_sincosf_poly(x * sign, x * x, (n & 2) != 0, n);
+}
+
+RT_FN float libm_cosf(float y) {
+    double x = double(y);
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+    if (top < 0x3f4u) {
+        if (top < 0x398u) {
+            return 1.0f;
+        }
+        return libm_sincosf_poly(x, x * x, false, 1);
+    }
+    const double r = x * 0x1.45F306DC9C883p+23;
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = x - double(n) * 0x1.921FB54442D18p0;
+    const int m = n + 1;
+    const double sign = ((m & 3) == 1 || (m & 3) == 2) ? -1.0 : 1.0;
+    return libm_sincosf_poly(x * sign, x * x, (m & 2) != 0, n ^ 1);
+}
+
+RT_FN float libm_atanf(float x) {
+    const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f, hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
+    const float lo0 = 5.0121582440e-09f, lo1 = 3.7748947079e-08f, lo2 = 3.4473217170e-08f, lo3 = 7.5497894159e-08f;
+    const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+                aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+                aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+    const int hx = __float_as_int(x);
+    const int ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c800000) { // |x| >= 2^26
+        if (ix > 0x7f800000) {
+            return x + x;
+        }
+        return (hx > 0) ? (hi3 + lo3) : (-hi3 - lo3);
+    }
+    if (ix < 0x3ee00000) { // |x| < 0.4375
+        if (ix < 0x31000000) { // |x| < 2^-29
+            return x;
+        }
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) { // |x| < 1.1875
+            if (ix < 0x3f300000) { // 7/16 <= |x| < 11/16
+                id = 0;
+                x = (2.0f * x - 1.0f) / (2.0f + x);
+            } else {
+                id = 1;
+                x = (x - 1.0f) / (x + 1.0f);
+            }
+        } else {
+            if (ix < 0x401c0000) { // |x| < 2.4375
+                id = 2;
+                x = (x - 1.5f) / (1.0f + 1.5f * x);
+            } else {
+                id = 3;
+                x = -1.0f / x;
+            }
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    const float s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (id < 0) {
+        return x - x * (s1 + s2);
+    }
+    const float hi = (id == 0) ? hi0 : ((id == 1) ? hi1 : ((id == 2) ? hi2 : hi3));
+    const float lo = (id == 0) ? lo0 : ((id == 1) ? lo1 : ((id == 2) ? lo2 : lo3));
+    const float r = hi - ((x * (s1 + s2) - lo) - x);
+    return (hx < 0) ? -r : r;
+}
+
+RT_FN float libm_atan2f(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+                pi_lo = -8.7422776573e-08f;
+    const int hx = __float_as_int(x), hy = __float_as_int(y);
+    const int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) {
+        return x + y;
+    }
+    if (hx == 0x3f800000) {
+        return libm_atanf(y);
+    }
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) {
+        return (m < 2) ? y : ((m == 2) ? (pi + tiny) : (-pi - tiny));
+    }
+    if (ix == 0) {
+        return (hy < 0) ? (-pi_o_2 - tiny) : (pi_o_2 + tiny);
+    }
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) {
+            return (m == 0) ? (pi_o_4 + tiny) : ((m == 1) ? (-pi_o_4 - tiny) : ((m == 2) ? (3.0f * pi_o_4 + tiny) : (-3.0f * pi_o_4 - tiny)));
+        }
+        return (m == 0) ? 0.0f : ((m == 1) ? -0.0f : ((m == 2) ? (pi + tiny) : (-pi - tiny)));
+    }
+    if (iy == 0x7f800000) {
+        return (hy < 0) ? (-pi_o_2 - tiny) : (pi_o_2 + tiny);
+    }
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) {
+        z = pi_o_2 + 0.5f * pi_lo;
+    } else if (hx < 0 && k < -60) {
+        z = 0.0f;
+    } else {
+        z = libm_atanf(fabsf(y / x));
+    }
+    return (m == 0) ? z : ((m == 1) ? -z : ((m == 2) ? (pi - (z - pi_lo)) : ((z - pi_lo) - pi)));
+}
+
+// exp2f(float(e) - 128.0f) of rgbe_to_rgb (CoreRef.h:234-237): an exact power of two for every byte e
+RT_DEV float rgbe_scale(uint32_t e) {
+    const int n = int(e) - 128;
+    return (n >= -126) ? __int_as_float((n + 127) << 23) : __int_as_float(1 << (149 + n));
+}
+
 // CoreRef.cpp:771-802
 RT_DEV float approx_atan2(float y, float x) {
     float t0, t1, t3, t4;

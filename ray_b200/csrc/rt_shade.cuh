@@ -999,8 +999,18 @@ RT_DEV bool shade_surface_a(const bool tex_on, const PassSettings &ps, float lim
         const float pdf_factor =
             (total_depth(ray.depth) < ps.max_total_depth) ? safe_div_pos(1.0f, inter.u) : -1.0f;
         c4 env_col = c4{1.0f, 1.0f, 1.0f, 1.0f};
+        const SceneEnv &env = sc.lights.env;
+        const uint32_t env_map = is_indirect(ray.depth) ? env.env_map : env.back_map;
+        const float env_map_rotation = is_indirect(ray.depth) ? env.env_map_rotation : env.back_map_rotation;
+        if (tex_on && env_map != kTexInvalid) {
+            const v2 tex_rand = rand2d(rand_dim + kRandDimTex, rand_hash, iteration - 1, sc.rand_seq);
+            const v3 m = sample_latlong_rgbe(sc.tex, env_map, I, env_map_rotation, tex_rand);
+            env_col = c4{m.x, m.y, m.z, 1.0f};
+        }
         if (sc.lights.env_light_index != 0xffffffffu && pdf_factor >= 0.0f && is_indirect(ray.depth)) {
-            const float light_pdf = safe_div_pos(0.5f, kPi * pdf_factor);
+            const float light_pdf = (tex_on && env.qtree_levels != 0)
+                                        ? safe_div_pos(evaluate_env_qtree(env, env_map_rotation, I), pdf_factor)
+                                        : safe_div_pos(0.5f, kPi * pdf_factor);
             const float bsdf_pdf = ray.pdf;
             const float mis_weight = power_heuristic(bsdf_pdf, light_pdf);
             env_col.x *= mis_weight;
@@ -1037,7 +1047,12 @@ RT_DEV bool shade_surface_a(const bool tex_on, const PassSettings &ps, float lim
         const float pdf_factor = 1.0f / inter.u;
         v3 lcol = mk3(l.col);
         if (l_sky_portal(l)) {
-            lcol *= mk3(sc.lights.env_col);
+            v3 env_col = mk3(sc.lights.env_col);
+            if (tex_on && sc.lights.env.env_map != kTexInvalid) {
+                const v2 tex_rand = rand2d(rand_dim + kRandDimTex, rand_hash, iteration - 1, sc.rand_seq);
+                env_col *= sample_latlong_rgbe(sc.tex, sc.lights.env.env_map, I, sc.lights.env.env_map_rotation, tex_rand);
+            }
+            lcol *= env_col;
         }
         const int type = l_type(l);
         if (type == LIGHT_SPHERE) {

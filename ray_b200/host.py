@@ -129,9 +129,12 @@ class Scene:
         except Exception:
             pass
 
-    def set_environment(self, env_col, back_col, importance_sample=True):
+    def set_environment(self, env_col, back_col, importance_sample=True, env_map=capi.RS_INVALID,
+                        back_map=capi.RS_INVALID, env_map_rotation=0.0, back_map_rotation=0.0):
         d = capi.rs_environment_desc(env_col=tuple(env_col), back_col=tuple(back_col),
-                                     importance_sample=1 if importance_sample else 0)
+                                     importance_sample=1 if importance_sample else 0, env_map=env_map,
+                                     back_map=back_map, env_map_rotation=env_map_rotation,
+                                     back_map_rotation=back_map_rotation)
         self.lib.rh_set_environment(self.h, C.byref(d))
 
     def add_texture(self, pixels, is_srgb=True, is_normalmap=False, generate_mipmaps=False, reconstruct_z=False,

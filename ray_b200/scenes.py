@@ -42,6 +42,10 @@ class SceneDesc:
     env_col: tuple = (0.0, 0.0, 0.0)
     back_col: tuple = (0.0, 0.0, 0.0)
     env_importance_sample: bool = True
+    env_map: int = capi.RS_INVALID  # index into `textures` of an RGBE lat-long map (RGBA8888), or RS_INVALID
+    back_map: int = capi.RS_INVALID
+    env_map_rotation: float = 0.0
+    back_map_rotation: float = 0.0
     camera: capi.rs_camera_desc = None
     textures: list = field(default_factory=list)  # (uint8 array (h, w, c), flags dict); material descs refer by index
 
@@ -63,8 +67,11 @@ class SceneDesc:
 
 def build(desc: SceneDesc, backend):
     """Replay `desc` on `backend`; returns the backend (finalized)."""
-    backend.set_environment(desc.env_col, desc.back_col, desc.env_importance_sample)
     tex_ids = [backend.add_texture(px, **flags) for px, flags in desc.textures]
+    backend.set_environment(desc.env_col, desc.back_col, desc.env_importance_sample,
+                            env_map=tex_ids[desc.env_map] if desc.env_map != capi.RS_INVALID else capi.RS_INVALID,
+                            back_map=tex_ids[desc.back_map] if desc.back_map != capi.RS_INVALID else capi.RS_INVALID,
+                            env_map_rotation=desc.env_map_rotation, back_map_rotation=desc.back_map_rotation)
 
     def with_textures(d, fields):
         """texture fields hold indices into desc.textures -> translate to backend handles (on a copy)"""
@@ -539,4 +546,48 @@ def textured(width=96, height=72) -> SceneDesc:
     fwd /= np.linalg.norm(fwd)
     s.camera = capi.rs_camera_desc.default(origin=(0.0, 2.2, 6.5), fwd=tuple(fwd.astype(np.float32)), fov=40.0,
                                            filter=capi.FILTER_BOX, max_diff_depth=4, max_total_depth=8)
+    return s
+
+
+def rgbe_image(rgb):
+    """float RGB (h, w, 3) -> RGBE bytes (h, w, 4), Ward's encoding (what the reference's rgbe_to_rgb decodes)."""
+    rgb = np.asarray(rgb, dtype=np.float64)
+    m = rgb.max(axis=-1)
+    e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, -128)
+    scale = np.where(m > 1e-32, 256.0 / np.exp2(e), 0.0)
+    out = np.zeros(rgb.shape[:2] + (4,), np.uint8)
+    out[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8)
+    out[..., 3] = np.clip(e + 128, 0, 255).astype(np.uint8)
+    return out
+
+
+def envmap_zoo(width=128, height=96, importance_sample=True, rotation=0.7) -> SceneDesc:
+    """material_zoo lit by a lat-long RGBE environment map: a sky gradient with a small,
+    very bright sun, so the importance-sampling quad-tree has several levels; the same map (rotated differently) is the
+    background camera rays see; one rect light is a sky portal."""
+    s = material_zoo(width, height, lights=("sphere",), env=(1.0, 1.0, 1.0), filter=capi.FILTER_BOX)
+    s.name = "envmap_zoo"
+    w, h = 128, 64
+    v, u = np.mgrid[0:h, 0:w]
+    theta = (v + 0.5) / h * np.pi
+    phi = (u + 0.5) / w * 2 * np.pi
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)], axis=-1)
+    up = np.clip(d[..., 1], 0.0, 1.0)
+    sky = np.stack([0.25 + 0.25 * up, 0.35 + 0.35 * up, 0.5 + 0.6 * up], axis=-1) * 0.6
+    sky = np.where(d[..., 1:2] < 0.0, np.asarray([0.12, 0.10, 0.08]), sky)
+    sun_dir = np.asarray([0.5, 0.65, 0.57])
+    sun_dir = sun_dir / np.linalg.norm(sun_dir)
+    sun = np.clip((d @ sun_dir - 0.985) / 0.015, 0.0, 1.0) ** 2
+    img = sky + sun[..., None] * np.asarray([90.0, 80.0, 60.0])
+    t_env = s.add_texture(rgbe_image(img), is_srgb=False)
+    s.env_map = t_env
+    s.back_map = t_env
+    s.env_map_rotation = rotation
+    s.back_map_rotation = rotation * 0.5
+    s.env_importance_sample = importance_sample
+    M = np.eye(4)
+    M[:3, 3] = (-2.0, 3.0, 1.0)
+    s.lights.append(("rect", capi.rs_rect_light_desc(c=capi.rs_light_common.default(color=(1.0, 1.0, 1.0)), width=1.5,
+                                                     height=1.0, doublesided=0, sky_portal=1,
+                                                     xform=tuple(M.T.astype(np.float32).reshape(16)))))
     return s

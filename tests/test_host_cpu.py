@@ -209,6 +209,26 @@ def test_textures_and_textured_materials_match_reference(oracle_mod):
     osc.close()
 
 
+def test_environment_quadtree_matches_reference(oracle_mod):
+    """SURVEY 8(f)-2 on the host side: the stand-alone scene's restatement of PrepareEnvMapQTree gives the reference's
+    quad-tree bit for bit (same libm, same summation order), and the same environment fields."""
+    desc = scenes.envmap_zoo(32, 24)
+    hs = scenes.build(desc, host.Scene(None))
+    osc = scenes.build(desc, oracle_mod.Scene(wide=True))
+    assert host.load_library().rh_error_count(None) == 0, host.load_library().rh_last_error(None)
+    hv, ov = hs.view(), osc.view()
+    assert hv.qtree_levels == ov.qtree_levels >= 3
+    assert (hv.env_map, hv.back_map, hv.env_light_index) == (ov.env_map, ov.back_map, ov.env_light_index)
+    assert (hv.env_map_rotation, hv.back_map_rotation) == (ov.env_map_rotation, ov.back_map_rotation)
+    for i in range(ov.qtree_levels):
+        n = 4 ** (ov.qtree_levels - 1 - i) * 4
+        a = np.ctypeslib.as_array(C.cast(ov.qtree_mips[i], C.POINTER(C.c_uint32)), shape=(n,))
+        b = np.ctypeslib.as_array(C.cast(hv.qtree_mips[i], C.POINTER(C.c_uint32)), shape=(n,))
+        assert np.array_equal(a, b), f"quad-tree level {i}"
+    hs.close()
+    osc.close()
+
+
 def test_filter_tables_match_reference(oracle_mod):
     for filt, width in ((capi.FILTER_GAUSSIAN, 1.5), (capi.FILTER_BLACKMAN_HARRIS, 1.5), (capi.FILTER_BLACKMAN_HARRIS, 2.0)):
         desc = scenes.cornell_box(16, 16)

@@ -29,6 +29,7 @@ def _block_mean(img, b):
                                        extra_lights=6), 192),
     ("instanced", lambda: scenes.instanced(25, 300, 96, 96), 128),
     ("textured", lambda: scenes.textured(96, 72), 192),
+    ("envmap_zoo", lambda: scenes.envmap_zoo(96, 72), 192),
 ])
 def test_host_layer_matches_reference_renderer(oracle_mod, name, make, spp):
     desc = make()

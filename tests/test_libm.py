@@ -1,4 +1,6 @@
-"""CPU: the float-only acosf restatement used on the device (rt_math.cuh: libm_acosf, glibc 2.39
+"""CPU: libm restatements used on the device against the host libm the reference links.
+sinf / cosf / atanf / atan2f (environment maps) are extracted from rt_math.cuh and compared on tens of millions of
+arguments of the range the path produces; acosf: the float-only acosf restatement used on the device (rt_math.cuh: libm_acosf, glibc 2.39
 sysdeps/ieee754/flt-32/e_acosf.c) against the host libm the reference links, on a dense sample of [-1, 1] plus edge
 cases.  (The full 2^31-point sweep was run once when the port was written: 0 mismatches.)"""
 import os
@@ -37,6 +39,52 @@ int main(void){
     f = tmp_path / "acos.c"
     f.write_text(c)
     exe = tmp_path / "acos"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(f), "-lm"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    sys.stdout.write(out.stdout)
+    assert out.returncode == 0, out.stdout
+
+
+def test_device_trig_restatements_match_host_libm(tmp_path):
+    """libm_sinf / libm_cosf / libm_atanf / libm_atan2f (rt_math.cuh), compiled as C, against sinf / cosf / atanf / atan2f."""
+    src = open(os.path.join(ROOT, "ray_b200", "csrc", "rt_math.cuh")).read()
+    i0 = src.index("RT_FN float libm_sincosf_poly(")
+    i1 = src.index("// exp2f(float(e) - 128.0f) of rgbe_to_rgb")
+    code = src[i0:i1].replace("RT_FN", "static")
+    c = r'''
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+#include <stdbool.h>
+static inline int __float_as_int(float f){int i;memcpy(&i,&f,4);return i;}
+static inline uint32_t __float_as_uint(float f){uint32_t i;memcpy(&i,&f,4);return i;}
+static inline float __int_as_float(int i){float f;memcpy(&f,&i,4);return f;}
+static inline int __double2int_rz(double d){return (int)d;}
+#define double(x) ((double)(x))
+#define float(x) ((float)(x))
+''' + code + r'''
+static uint32_t rng=12345; static uint32_t r32(void){ rng^=rng<<13; rng^=rng>>17; rng^=rng<<5; return rng; }
+static double u01(void){ return (double)r32()/4294967296.0; }
+int main(void){ long bad=0;
+  for(long i=0;i<8000000;i++){
+    float x=(float)(u01()*16.0-8.0); volatile float xv=x;
+    if(__float_as_int(sinf(xv))!=__float_as_int(libm_sinf(x))){ if(bad<5)printf("sinf %a\n",x); bad++; }
+    if(__float_as_int(cosf(xv))!=__float_as_int(libm_cosf(x))){ if(bad<5)printf("cosf %a\n",x); bad++; }
+    float t=(float)(u01()*60.0-30.0); volatile float tv=t;
+    if(__float_as_int(atanf(tv))!=__float_as_int(libm_atanf(t))){ if(bad<5)printf("atanf %a\n",t); bad++; }
+    float yy=(float)(u01()*2.0-1.0), xx=(float)(u01()*2.0-1.0); volatile float yv=yy, xw=xx;
+    if(__float_as_int(atan2f(yv,xw))!=__float_as_int(libm_atan2f(yy,xx))){ if(bad<5)printf("atan2f %a %a\n",yy,xx); bad++; } }
+  const float e[]={0.0f,-0.0f,1.0f,-1.0f,0x1p-13f,0x1p-12f,0.78539813f,0.7853982f,0.78539824f,3.1415927f,6.2831855f,6.9831855f,-6.9831855f,1e-30f,0.4375f,0.6875f,1.1875f,2.4375f,1e10f};
+  for(unsigned i=0;i<sizeof(e)/sizeof(e[0]);i++) for(unsigned j=0;j<sizeof(e)/sizeof(e[0]);j++){ volatile float a=e[i], b=e[j];
+    if(__float_as_int(atan2f(a,b))!=__float_as_int(libm_atan2f(e[i],e[j]))){ printf("atan2f edge %a %a\n",e[i],e[j]); bad++; }
+    if(i==0 && fabsf(e[j])<100.0f){ if(__float_as_int(sinf(b))!=__float_as_int(libm_sinf(e[j]))){ printf("sinf edge %a\n",e[j]); bad++; }
+      if(__float_as_int(cosf(b))!=__float_as_int(libm_cosf(e[j]))){ printf("cosf edge %a\n",e[j]); bad++; } } }
+  printf("bad=%ld\n",bad); return bad!=0; }
+'''
+    f = tmp_path / "trig.c"
+    f.write_text(c)
+    exe = tmp_path / "trig"
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(f), "-lm"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     sys.stdout.write(out.stdout)

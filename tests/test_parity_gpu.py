@@ -23,6 +23,9 @@ SCENES = {
     # every texture fetch on the path (base / roughness / metallic / specular / normal maps,
     # texture-driven Mix, alpha cut-out through the transparency loops, textured emissive triangles)
     "textured": lambda: scenes.textured(96, 72),
+    # RGBE lat-long environment map: miss shading, quad-tree importance sampling + MIS,
+    # a rotated background map for camera rays, a sky-portal rect light
+    "envmap_zoo": lambda: scenes.envmap_zoo(96, 72),
 }
 
 
