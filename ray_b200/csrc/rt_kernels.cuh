@@ -310,6 +310,45 @@ __global__ void __launch_bounds__(256) k_raygen(KParams p, RayBuf rays, HitBuf h
     }
 }
 
+// Work distribution of the persistent trace kernels.  A warp takes `pk` consecutive rays at a time: 32 when the list
+// is long, fewer when the list has less than 32 rays per resident warp (deep bounces), because the rays of a packet that
+// diverge are serialised and a short list is better spread thin over all warps.  The first packet of every warp is
+// static (no atomic); later ones come from the list's queue head, which therefore counts from 0 past the static part.
+struct PacketQueue {
+    uint32_t count, pk, static_end, next;
+    bool first;
+};
+
+RT_DEV PacketQueue packet_queue_init(uint32_t count) {
+    PacketQueue q;
+    q.count = count;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t pk = 32;
+    while (pk > 4 && uint64_t(pk / 2) * warps >= count) {
+        pk >>= 1;
+    }
+    q.pk = pk;
+    q.static_end = warps * pk;
+    q.next = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * pk;
+    q.first = true;
+    return q;
+}
+
+// returns false when the list is exhausted; else `base` = first ray of this warp's packet
+RT_DEV bool packet_queue_next(PacketQueue &q, uint32_t *head, int lane, uint32_t &base) {
+    if (q.first) {
+        q.first = false;
+        base = q.next;
+    } else {
+        uint32_t b = 0;
+        if (lane == 0) {
+            b = atomicAdd(head, q.pk);
+        }
+        base = q.static_end + __shfl_sync(0xffffffffu, b, 0);
+    }
+    return base < q.count;
+}
+
 // ---- TraceRays: IntersectScene (CoreRef.cpp:3041-3158) [+ IntersectAreaLights :3616-3860] ------------------------
 // Persistent warps pull 32-ray packets from a queue head; `bounce` selects the counter slot.
 // INIT_HITS: secondary lists start from the default "no intersection" record (RendererCPU.h:532-535) built in
@@ -321,17 +360,11 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_closest(KParams 
     const int lane = threadIdx.x & 31;
     TraverseCounters cnt{0, 0};
     StackEntry st[2 * kMaxStack];
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) {
-            base = atomicAdd(head, 32u);
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) {
-            break;
-        }
+    PacketQueue q = packet_queue_init(count);
+    uint32_t base;
+    while (packet_queue_next(q, head, lane, base)) {
         const uint32_t i = base + lane;
-        if (i < count) {
+        if (lane < q.pk && i < count) {
             const float4 a = rays.o_cw[i], dd = rays.d_cs[i];
             const uint2 xd = rays.xy_depth[i];
             const v3 r_o = v3{a.x, a.y, a.z};
@@ -564,17 +597,11 @@ __global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_shadow(KParams p
     const int lane = threadIdx.x & 31;
     TraverseCounters cnt{0, 0};
     StackEntry st[2 * kMaxStack];
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) {
-            base = atomicAdd(head, 32u);
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) {
-            break;
-        }
+    PacketQueue q = packet_queue_init(count);
+    uint32_t base;
+    while (packet_queue_next(q, head, lane, base)) {
         const uint32_t i = base + lane;
-        if (i < count) {
+        if (lane < q.pk && i < count) {
             const ShadowRayD r = load_shadow(srays, i);
             const v3 rd = r.d;
             v3 ro = r.o;
