@@ -154,6 +154,11 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *scene);
 
 int rc_render(rc_ctx *ctx, const rc_pass_desc *pass);
 int rc_sync(rc_ctx *ctx);
+/* RendererBase::DenoiseImage(const RegionContext &) (internal/RendererCPU.h:661-787): joint NLM filter (7x7 window,
+ * 3x3 patches, base-colour and depth-normals features) of the accumulated image inside `rect`; writes the filtered
+ * linear image to RC_BUF_RAW and its tonemapped version to RC_BUF_FINAL, updates required-samples.  Uses the variance
+ * threshold and gamma of the last rc_render; `iteration` = RegionContext::iteration.  Blocking. */
+int rc_denoise_nlm(rc_ctx *ctx, const rc_rect *rect, int iteration);
 /* dst: rect.w*rect.h RGBA float pixels written with the given pitch (in pixels). */
 int rc_readback(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch);
 int rc_readback_required_samples(rc_ctx *ctx, uint16_t *dst);

@@ -55,6 +55,8 @@ void rh_get_camera(rh_scene *s, rc_camera *out);
 /* RendererBase::RenderScene(scene, RegionContext{rect, *iteration}); *iteration is updated like region.iteration.
  * count > 1 = that many consecutive calls with one synchronisation at the end (Cuda::Renderer::RenderSceneBatch). */
 void rh_render(rh_renderer *r, rh_scene *s, const rc_rect *rect, int *iteration, int count);
+/* RendererBase::DenoiseImage(const RegionContext &): NLM filter of the region at RegionContext::iteration = iteration */
+void rh_denoise(rh_renderer *r, const rc_rect *rect, int iteration);
 /* which: 0 get_pixels_ref, 1 get_raw_pixels_ref, 2 aux BaseColor, 3 aux DepthNormals; borrowed pointer */
 const float *rh_get_pixels(rh_renderer *r, int which, int *pitch);
 void rh_get_stats(rh_renderer *r, uint64_t us[11]);

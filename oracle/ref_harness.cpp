@@ -596,6 +596,13 @@ void ro_render(ro_renderer *r, ro_scene *s, const rc_rect *rect, int *iteration)
     *iteration = region.iteration;
 }
 
+// RendererBase::DenoiseImage(const RegionContext &) (the NLM overload) over `rect` at RegionContext::iteration = iteration
+void ro_denoise(ro_renderer *r, const rc_rect *rect, int iteration) {
+    RegionContext region(rect_t{rect->x, rect->y, rect->w, rect->h});
+    region.iteration = iteration;
+    reinterpret_cast<OracleRenderer *>(r)->r->DenoiseImage(region);
+}
+
 // which: 0 final (tonemapped), 1 raw, 2 base colour, 3 depth-normals
 const float *ro_get_pixels(ro_renderer *r, int which, int *pitch) {
     RendererBase *rb = reinterpret_cast<OracleRenderer *>(r)->r.get();

@@ -259,7 +259,16 @@ color_data_rgba_t Renderer::get_aux_pixels_ref(const eAUXBuffer buf) const {
 }
 
 // out of the hot-path scope: report through the log like any backend missing a feature
-void Renderer::DenoiseImage(const RegionContext &) { log_->Error("Ray(CUDA): NLM denoising is not implemented by the CUDA backend"); }
+// reference internal/RendererCPU.h:661-787: joint NLM filter of the region (rt_denoise.cuh)
+void Renderer::DenoiseImage(const RegionContext &region) {
+    const rect_t &r = region.rect();
+    const rc_rect rr = {r.x, r.y, r.w, r.h};
+    if (rc_denoise_nlm(ctx_, &rr, region.iteration) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+        return;
+    }
+    final_dirty_ = raw_dirty_ = true;
+}
 void Renderer::DenoiseImage(int, const RegionContext &) { log_->Error("Ray(CUDA): UNet denoising is not implemented by the CUDA backend"); }
 void Renderer::UpdateSpatialCache(const SceneBase &, RegionContext &) { log_->Error("Ray(CUDA): the spatial cache is not implemented by the CUDA backend"); }
 void Renderer::ResolveSpatialCache(const SceneBase &, const ParallelFor &) { log_->Error("Ray(CUDA): the spatial cache is not implemented by the CUDA backend"); }

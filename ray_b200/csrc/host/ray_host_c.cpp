@@ -116,6 +116,11 @@ void rh_render(rh_renderer *r, rh_scene *s, const rc_rect *rect, int *iteration,
     }
     *iteration = region.iteration;
 }
+void rh_denoise(rh_renderer *r, const rc_rect *rect, int iteration) {
+    RegionContext region(rect_t{rect->x, rect->y, rect->w, rect->h});
+    region.iteration = iteration;
+    R(r)->DenoiseImage(region);
+}
 const float *rh_get_pixels(rh_renderer *r, int which, int *pitch) {
     color_data_rgba_t d{nullptr, 0};
     switch (which) {

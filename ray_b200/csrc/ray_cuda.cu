@@ -19,6 +19,7 @@
 
 #include "rt_kernels.cuh"
 #include "rt_sort.cuh"
+#include "rt_denoise.cuh"
 
 using namespace rt;
 
@@ -62,6 +63,9 @@ struct rc_ctx {
     DevArray wnodes, mtris, tri_indices, tri_materials, materials, mesh_instances, vertices, vtx_indices, lights,
         light_cwnodes;
     DevArray tex_descs, tex_texels, qtree;
+    float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
+    size_t nlm_scratch_elems = 0;
+    float last_inv_gamma = 1.0f, last_variance_threshold = 0.0f; // tonemap_params_ / variance_threshold_ of the reference
     SceneEnv env{};
     float *d_srgb_lut = nullptr;
     bool have_scene = false;
@@ -70,7 +74,7 @@ struct rc_ctx {
 
     bool stats_enabled = true;
     std::vector<cudaEvent_t> events;
-    cudaEvent_t user_events[8] = {};
+    cudaEvent_t user_events[10] = {}; // 0..7: rc_event_record slots, 8..9: rc_denoise_nlm timing
     struct PendingSample {
         int max_bounces;
     };
@@ -449,6 +453,8 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
                              : 0.0f;
         const int n = p.rect_w * p.rect_h;
         k_resolve<<<(n + 255) / 256, 256, 0, s>>>(p, exposure_mul, mix_factor, half_mix_factor, is_class_a, inv_gamma, vt);
+        ctx->last_inv_gamma = inv_gamma;
+        ctx->last_variance_threshold = vt;
         ctx->kernel_launches[KF_RESOLVE]++;
         k_accumulate_totals<<<1, 32, 0, s>>>(p, max_bounces);
     }
@@ -679,6 +685,7 @@ void rc_destroy(rc_ctx *ctx) {
     cudaFree(ctx->d_pmj);
     cudaFree(ctx->d_filter_table);
     cudaFree(ctx->d_srgb_lut);
+    cudaFree(ctx->nlm_scratch);
     for (DevArray *a : {&ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
                         &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {
@@ -998,6 +1005,56 @@ int rc_render(rc_ctx *ctx, const rc_pass_desc *pass) {
     }
     if ((pass->flags & RC_RENDER_ASYNC) == 0) {
         return rc_sync(ctx);
+    }
+    return 0;
+}
+
+int rc_denoise_nlm(rc_ctx *ctx, const rc_rect *rect, int iteration) {
+    if (!ctx || !rect) {
+        return fail(ctx, "rc_denoise_nlm: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    const rc_rect &r = *rect;
+    if (r.x < 0 || r.y < 0 || r.w <= 0 || r.h <= 0 || r.x + r.w > ctx->w || r.y + r.h > ctx->h) {
+        return fail(ctx, "rc_denoise_nlm: rect (%d,%d,%d,%d) is outside the %dx%d frame", r.x, r.y, r.w, r.h, ctx->w, ctx->h);
+    }
+    NlmParams p{};
+    p.fb = ctx->fb;
+    p.rx = r.x, p.ry = r.y, p.rw = r.w, p.rh = r.h;
+    p.ex = r.x - kNlmExt, p.ey = r.y - kNlmExt, p.ew = r.w + 2 * kNlmExt, p.eh = r.h + 2 * kNlmExt;
+    const size_t plane = size_t(p.ew) * p.eh;
+    if (ctx->nlm_scratch_elems < 3 * plane) {
+        cudaFree(ctx->nlm_scratch);
+        ctx->nlm_scratch = nullptr;
+        ctx->nlm_scratch_elems = 0;
+        CU_CHECK(ctx, cudaMalloc(&ctx->nlm_scratch, 3 * plane * sizeof(float4)));
+        ctx->nlm_scratch_elems = 3 * plane;
+    }
+    p.temp_final = ctx->nlm_scratch;
+    p.var_h = ctx->nlm_scratch + plane;
+    p.var_f = ctx->nlm_scratch + 2 * plane;
+    p.variance_threshold = ctx->last_variance_threshold;
+    p.iteration = iteration;
+    p.inv_gamma = ctx->last_inv_gamma;
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0 = ctx->user_events[8], e1 = ctx->user_events[9];
+    if (e0 && e1) {
+        cudaEventRecord(e0, s);
+    }
+    k_nlm_prep<<<unsigned((plane + 255) / 256), 256, 0, s>>>(p);
+    const size_t inner = size_t(p.ew - 8) * (p.eh - 8);
+    k_nlm_vblur<<<unsigned((inner + 255) / 256), 256, 0, s>>>(p);
+    k_nlm_filter<<<dim3((r.w + kNlmBx - 1) / kNlmBx, (r.h + kNlmBy - 1) / kNlmBy), dim3(kNlmBx, kNlmBy), 0, s>>>(p);
+    if (e0 && e1) {
+        cudaEventRecord(e1, s);
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    CU_CHECK(ctx, cudaGetLastError());
+    if (e0 && e1) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
+            ctx->stats_us[8] += uint64_t(ms * 1000.0f); // stats_t::time_denoise_us
+        }
     }
     return 0;
 }

@@ -414,6 +414,45 @@ RT_FN float libm_atan2f(float y, float x) {
     return (m == 0) ? z : ((m == 1) ? -z : ((m == 2) ? (pi - (z - pi_lo)) : ((z - pi_lo) - pi)));
 }
 
+// expf of the host libm (glibc 2.39 sysdeps/ieee754/flt-32/e_expf.c, the Arm optimized-routines algorithm: 2^(k/32) table
+// times a cubic in double precision).  The NLM denoiser's weights are expf(-distance) (DenoiseRef.cpp:55,76).  The table is
+// T[i] = bits(2^(i/32)) - (i << 47), regenerated from its definition; tests/test_libm.py compares with the host expf.
+RT_FN float libm_expf(float x) {
+    static const uint64_t T[32] = {0x3ff0000000000000ULL,0x3fefd9b0d3158574ULL,0x3fefb5586cf9890fULL,0x3fef9301d0125b51ULL,0x3fef72b83c7d517bULL,0x3fef54873168b9aaULL,0x3fef387a6e756238ULL,0x3fef1e9df51fdee1ULL,0x3fef06fe0a31b715ULL,0x3feef1a7373aa9cbULL,0x3feedea64c123422ULL,0x3feece086061892dULL,0x3feebfdad5362a27ULL,0x3feeb42b569d4f82ULL,0x3feeab07dd485429ULL,0x3feea47eb03a5585ULL,0x3feea09e667f3bcdULL,0x3fee9f75e8ec5f74ULL,0x3feea11473eb0187ULL,0x3feea589994cce13ULL,0x3feeace5422aa0dbULL,0x3feeb737b0cdc5e5ULL,0x3feec49182a3f090ULL,0x3feed503b23e255dULL,0x3feee89f995ad3adULL,0x3feeff76f2fb5e47ULL,0x3fef199bdd85529cULL,0x3fef3720dcef9069ULL,0x3fef5818dcfba487ULL,0x3fef7c97337b9b5fULL,0x3fefa4afa2a490daULL,0x3fefd0765b6e4540ULL};
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+    const double xd = double(x);
+    const uint32_t abstop = (__float_as_uint(x) >> 20) & 0x7ffu;
+    if (abstop >= 0x42bu) { // |x| >= 88 or NaN
+        if (__float_as_uint(x) == 0xff800000u) {
+            return 0.0f;
+        }
+        if (abstop >= 0x7f8u) {
+            return x + x;
+        }
+        if (x > 0x1.62e42ep6f) {
+            return __uint_as_float(0x7f800000u);
+        }
+        if (x < -0x1.9fe368p6f) {
+            return 0.0f;
+        }
+    }
+    double z = InvLn2N * xd;
+    double kd = z + SHIFT;
+    const uint64_t ki = uint64_t(__double_as_longlong(kd));
+    kd -= SHIFT;
+    const double r = z - kd;
+    uint64_t t = T[ki % 32];
+    t += ki << (52 - 5);
+    const double s = __longlong_as_double((long long)t);
+    z = C0 * r + C1;
+    const double r2 = r * r;
+    double y = C2 * r + 1;
+    y = z * r2 + y;
+    y = y * s;
+    return float(y);
+}
+
 // exp2f(float(e) - 128.0f) of rgbe_to_rgb (CoreRef.h:234-237): an exact power of two for every byte e
 RT_DEV float rgbe_scale(uint32_t e) {
     const int n = int(e) - 128;

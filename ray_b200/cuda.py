@@ -44,6 +44,7 @@ def load_library():
         "rc_upload_tables": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int]),
         "rc_upload_scene": (C.c_int, [vp, P(capi.rc_scene_view)]),
         "rc_render": (C.c_int, [vp, P(capi.rc_pass_desc)]),
+        "rc_denoise_nlm": (C.c_int, [vp, P(capi.rc_rect), C.c_int]),
         "rc_sync": (C.c_int, [vp]),
         "rc_readback": (C.c_int, [vp, C.c_int, P(capi.rc_rect), vp, C.c_int]),
         "rc_readback_required_samples": (C.c_int, [vp, vp]),
@@ -76,7 +77,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "rc_device_count", "rc_create", "rc_destroy", "rc_last_error", "rc_device_name", "rc_resize", "rc_clear",
-    "rc_upload_tables", "rc_upload_scene", "rc_render", "rc_sync", "rc_readback", "rc_readback_required_samples",
+    "rc_upload_tables", "rc_upload_scene", "rc_render", "rc_denoise_nlm", "rc_sync", "rc_readback", "rc_readback_required_samples",
     "rc_enable_stats", "rc_get_stats", "rc_get_counters", "rc_reset_stats", "rc_get_kernel_ms",
     "rc_stage_generate_primary_rays", "rc_stage_trace_rays", "rc_stage_shade", "rc_stage_trace_shadow_rays",
     "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
@@ -150,6 +151,10 @@ class Context:
 
     def render(self, p: capi.rc_pass_desc):
         self._check(self.lib.rc_render(self._ctx, C.byref(p)), "rc_render")
+
+    def denoise_nlm(self, rect, iteration):
+        r = capi.rc_rect(*rect)
+        self._check(self.lib.rc_denoise_nlm(self._ctx, C.byref(r), int(iteration)), "rc_denoise_nlm")
 
     def sync(self):
         self._check(self.lib.rc_sync(self._ctx), "rc_sync")

@@ -22,7 +22,7 @@ FINAL, RAW, BASE_COLOR, DEPTH_NORMALS = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
     "rh_create_renderer", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
-    "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_add_texture", "rh_add_material_node",
+    "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_denoise", "rh_add_texture", "rh_add_material_node",
     "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_add_light_directional",
     "rh_add_light_sphere", "rh_add_light_spot", "rh_add_light_rect", "rh_add_light_disk", "rh_add_light_line",
     "rh_add_camera", "rh_finalize", "rh_triangle_count", "rh_node_count", "rh_scene_view", "rh_get_camera", "rh_render",
@@ -55,6 +55,7 @@ def load_library():
         "rh_destroy_scene": (None, [vp]),
         "rh_set_environment": (None, [vp, P(capi.rs_environment_desc)]),
         "rh_add_texture": (u32, [vp, P(capi.rs_tex_desc)]),
+        "rh_denoise": (None, [vp, P(capi.rc_rect), C.c_int]),
         "rh_add_material_node": (u32, [vp, P(capi.rs_shading_node_desc)]),
         "rh_add_material_principled": (u32, [vp, P(capi.rs_principled_mat_desc)]),
         "rh_add_mesh": (u32, [vp, P(capi.rs_mesh_desc)]),
@@ -254,6 +255,12 @@ class Renderer:
         self.lib.rh_render(self.h, scene.h, C.byref(r), C.byref(it), count)
         self.check()
         return it.value
+
+    def denoise(self, rect, iteration):
+        """RendererBase::DenoiseImage(region): joint NLM filter; results through pixels(FINAL) / pixels(RAW)."""
+        r = capi.rc_rect(*rect)
+        self.lib.rh_denoise(self.h, C.byref(r), int(iteration))
+        self.check()
 
     def pixels(self, which=RAW, copy=True):
         """RendererBase::get_pixels_ref / get_raw_pixels_ref / get_aux_pixels_ref: reads the plane back into the

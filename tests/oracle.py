@@ -57,6 +57,7 @@ def load():
         "ro_renderer_destroy": (None, [vp]),
         "ro_renderer_clear": (None, [vp, P(C.c_float)]),
         "ro_render": (None, [vp, vp, P(capi.rc_rect), P(C.c_int)]),
+        "ro_denoise": (None, [vp, P(capi.rc_rect), C.c_int]),
         "ro_get_pixels": (P(C.c_float), [vp, C.c_int, P(C.c_int)]),
         "ro_get_stats": (None, [vp, P(C.c_uint64)]),
         "ro_render_mt": (C.c_double, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -314,6 +315,11 @@ class Renderer:
         it = C.c_int(iteration)
         self.lib.ro_render(self.h, scene.h, C.byref(r), C.byref(it))
         return it.value
+
+    def denoise(self, rect, iteration):
+        """RendererBase::DenoiseImage(region) (NLM)."""
+        r = capi.rc_rect(*rect)
+        self.lib.ro_denoise(self.h, C.byref(r), int(iteration))
 
     def pixels(self, which=1):
         pitch = C.c_int(0)

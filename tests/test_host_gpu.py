@@ -97,6 +97,39 @@ def test_regions_and_resize(oracle_mod):
     r.close()
 
 
+def test_denoise_image_through_the_renderer_api(oracle_mod):
+    """RendererBase::DenoiseImage(region) on the stand-alone renderer: runs without an ILog error, smooths the image
+    (lower high-frequency energy than the noisy input) and agrees with the reference's NLM of ITS render of the same scene
+    on the image mean (the two renders are statistically, not bitwise, equal: different BVH builders)."""
+    desc = scenes.cornell_box(96, 96)
+    w, h, spp = 96, 96, 16
+    osc = scenes.build(desc, oracle_mod.Scene(wide=False))
+    ref = oracle_mod.Renderer(capi.RT_REFERENCE, w, h)
+    it = 0
+    for _ in range(spp):
+        it = ref.render(osc, (0, 0, w, h), it)
+    ref.denoise((0, 0, w, h), it)
+    ref_img = ref.pixels(0)[..., :3].copy()
+    r = host.Renderer(w, h)
+    s = scenes.build(desc, r.create_scene())
+    it2 = r.render(s, (0, 0, w, h), 0, spp)
+    noisy = r.pixels(host.FINAL)[..., :3].copy()
+    r.denoise((0, 0, w, h), it2)
+    den = r.pixels(host.FINAL)[..., :3].copy()
+    assert np.isfinite(den).all()
+
+    def hf(a):
+        return float(np.abs(a[1:, 1:] - a[:-1, 1:]).mean() + np.abs(a[1:, 1:] - a[1:, :-1]).mean())
+
+    assert hf(den) < 0.8 * hf(noisy)
+    assert abs(float(den.mean()) - float(ref_img.mean())) < 0.03 * float(ref_img.mean())
+    assert r.stats_us()[8] > 0  # stats_t::time_denoise_us
+    s.close()
+    r.close()
+    ref.close()
+    osc.close()
+
+
 def test_unsupported_features_are_reported_not_faked():
     """A material that names a texture the scene does not have must fail the upload, not render untextured."""
     desc = scenes.cornell_box(16, 16)

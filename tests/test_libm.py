@@ -49,7 +49,7 @@ def test_device_trig_restatements_match_host_libm(tmp_path):
     """libm_sinf / libm_cosf / libm_atanf / libm_atan2f (rt_math.cuh), compiled as C, against sinf / cosf / atanf / atan2f."""
     src = open(os.path.join(ROOT, "ray_b200", "csrc", "rt_math.cuh")).read()
     i0 = src.index("RT_FN float libm_sincosf_poly(")
-    i1 = src.index("// exp2f(float(e) - 128.0f) of rgbe_to_rgb")
+    i1 = src.index("// expf of the host libm (glibc 2.39")
     code = src[i0:i1].replace("RT_FN", "static")
     c = r'''
 #include <math.h>
@@ -85,6 +85,43 @@ int main(void){ long bad=0;
     f = tmp_path / "trig.c"
     f.write_text(c)
     exe = tmp_path / "trig"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(f), "-lm"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    sys.stdout.write(out.stdout)
+    assert out.returncode == 0, out.stdout
+
+
+def test_device_expf_restatement_matches_host_libm(tmp_path):
+    """libm_expf (rt_math.cuh; the NLM denoiser's weights), compiled as C, against the host expf on the argument range
+    the filter produces (<= 0) plus positive and overflow / underflow edge cases."""
+    src = open(os.path.join(ROOT, "ray_b200", "csrc", "rt_math.cuh")).read()
+    i0 = src.index("RT_FN float libm_expf(float x) {")
+    i1 = src.index("// exp2f(float(e) - 128.0f) of rgbe_to_rgb")
+    code = src[i0:i1].replace("RT_FN", "static")
+    c = r'''
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+static inline uint32_t __float_as_uint(float f){uint32_t i;memcpy(&i,&f,4);return i;}
+static inline float __uint_as_float(uint32_t i){float f;memcpy(&f,&i,4);return f;}
+static inline long long __double_as_longlong(double d){long long i;memcpy(&i,&d,8);return i;}
+static inline double __longlong_as_double(long long i){double d;memcpy(&d,&i,8);return d;}
+#define double(x) ((double)(x))
+#define float(x) ((float)(x))
+#define uint64_t(x) ((uint64_t)(x))
+''' + code + r'''
+static uint32_t rng=777; static uint32_t r32(void){ rng^=rng<<13; rng^=rng>>17; rng^=rng<<5; return rng; }
+int main(void){ long bad=0;
+  for(long i=0;i<20000000;i++){ float x=-(float)((double)r32()/4294967296.0*112.0); if(i&1) x=-(float)((double)r32()/4294967296.0*4.0); if((i&15)==3) x=-x*20.0f;
+    volatile float xv=x; float a=expf(xv), b=libm_expf(x); if(__float_as_uint(a)!=__float_as_uint(b)){ if(bad<5)printf("x=%a %a %a\n",x,a,b); bad++; } }
+  const float e[]={0.0f,-0.0f,88.0f,88.72f,89.0f,-87.0f,-88.0f,-100.0f,-103.9f,-104.0f,-150.0f,-1e30f,1e-30f,-1e-30f};
+  for(unsigned i=0;i<sizeof(e)/sizeof(e[0]);i++){ volatile float xv=e[i]; if(__float_as_uint(expf(xv))!=__float_as_uint(libm_expf(e[i]))){ printf("edge %a\n",e[i]); bad++; } }
+  printf("bad=%ld\n",bad); return bad!=0; }
+'''
+    f = tmp_path / "expf.c"
+    f.write_text(c)
+    exe = tmp_path / "expf"
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(f), "-lm"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     sys.stdout.write(out.stdout)

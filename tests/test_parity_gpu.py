@@ -182,3 +182,34 @@ def test_adaptive_sampling_matches_reference_renderer(oracle_mod):
     c = pair.ctx.counters()
     assert c["primary_rays"] < spp * pair.w * pair.h, "no pixel converged: the adaptive path was not exercised"
     pair.close()
+
+
+def test_nlm_denoise_matches_reference_renderer(oracle_mod):
+    """RendererBase::DenoiseImage(region) (SURVEY 8(f)-3, NLM half): same 8 spp accumulated on both sides (bit-identical,
+    see above), then the joint NLM filter.  The filtered LINEAR image must be bit-identical (the weights go through a
+    restated libm expf); the tonemapped plane goes through powf (tolerance as for rc_render).  A sub-rect call checks
+    the clamped fetches at region borders that are not image borders."""
+    desc = scenes.cornell_box(96, 80)
+    pair = Pair(oracle_mod, desc)
+    spp = 8
+    ref = oracle_mod.Renderer(capi.RT_REFERENCE, pair.w, pair.h)
+    it = 0
+    for _ in range(spp):
+        it = ref.render(pair.osc, (0, 0, pair.w, pair.h), it)
+    pair.ctx.clear((0, 0, 0, 0))
+    for i in range(1, spp + 1):
+        pair.ctx.render(pair.make_pass(i))
+    assert bits_equal(pair.ctx.readback(capi.RC_BUF_RAW), ref.pixels(1))
+    for rect in ((0, 0, pair.w, pair.h), (17, 9, 40, 33)):
+        ref.denoise(rect, it)
+        pair.ctx.denoise_nlm(rect, it)
+        ref_raw, ref_final = ref.pixels(1), ref.pixels(0)
+        raw, final = pair.ctx.readback(capi.RC_BUF_RAW), pair.ctx.readback(capi.RC_BUF_FINAL)
+        x, y, w, h = rect
+        sl = (slice(y, y + h), slice(x, x + w))
+        assert np.isfinite(raw[sl]).all()
+        d = np.abs(raw[sl] - ref_raw[sl])
+        assert bits_equal(raw[sl], ref_raw[sl]), f"rect {rect}: filtered linear image L-inf {d.max()}, {int((d > 0).any(-1).sum())} px"
+        assert np.abs(final[sl] - ref_final[sl]).max() <= 2e-6
+    ref.close()
+    pair.close()
