@@ -17,6 +17,8 @@ SCENES = {
     "zoo": lambda: scenes.material_zoo(),
     "zoo_env_dof": lambda: scenes.material_zoo(128, 96, lights=("rect", "sphere"), env=(0.4, 0.5, 0.7),
                                                filter=capi.FILTER_BLACKMAN_HARRIS, fstop=2.0),
+    # hexagonal, rotated, anamorphic aperture + sensor shift + radiance clamps + exposure / gamma
+    "zoo_lens_clamp": lambda: _lens_clamp_scene(),
     "instanced": lambda: scenes.instanced(36, 600, 128, 96),
     "hall_small": lambda: scenes.hall("principled", 160, 90, floor_res=48, n_columns=8, col_seg=12, col_rings=8,
                                       extra_lights=12),
@@ -27,6 +29,18 @@ SCENES = {
     # a rotated background map for camera rays, a sky-portal rect light
     "envmap_zoo": lambda: scenes.envmap_zoo(96, 72),
 }
+
+
+def _lens_clamp_scene():
+    d = scenes.material_zoo(112, 80, lights=("spot", "disk", "line"), env=(0.2, 0.2, 0.25), filter=capi.FILTER_GAUSSIAN,
+                            fstop=1.4)
+    c = d.camera
+    c.lens_blades, c.lens_rotation, c.lens_ratio = 6, 0.3, 1.3
+    c.shift[0], c.shift[1] = 0.05, -0.03
+    c.clamp_direct, c.clamp_indirect = 2.0, 1.0
+    c.exposure, c.gamma = 0.5, 2.2
+    c.filter_width = 2.0
+    return d
 
 
 @pytest.fixture(scope="module", params=list(SCENES))
