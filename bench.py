@@ -129,11 +129,11 @@ def roofline(counters, kms, samples):
         "trace_closest": 56 * rays,
         # read ray 72 + hit 20; write 72/secondary ray + 48/shadow ray; radiance 16 W (primary) | 32 RMW (secondary);
         # primary AOVs 64 RMW
-        "shade": 92 * rays + 72 * sec + 48 * sh + 80 * prim + 32 * sec,
+        "shade": 92 * rays + 76 * sec + 48 * sh + 80 * prim + 32 * sec,  # 72 B ray + 4 B sort key per secondary ray
         # read 48 B shadow ray, RMW 32 B radiance
         "trace_shadow": 80 * sh,
-        # key 24 R + 4 W, scatter 76 R + 76 W
-        "sort": 180 * sec,
+        # scatter: key 4 R + ray 72 R + ray 72 W (keys and the histogram are produced by the shade kernel)
+        "sort": 148 * sec,
         # temp 16 R, full 32 RMW, half 32 RMW (every other iteration), raw 16 W, final 16 W, variance 16 W, req 4
         "resolve": 124 * (prim // max(samples, 1)) * samples,
         "raygen": 92 * prim,
