@@ -59,6 +59,17 @@ template <typename LeafFn>
 uint32_t CollapseToWide(const std::vector<BinaryNode> &nodes, uint32_t node, std::vector<rt::WNode> &out, uint32_t base,
                         LeafFn &&leaf_payload);
 
+// SAH-optimal collapse of a binary BVH (built down to single primitives) into 8-wide nodes: the dynamic programme of
+// Ylitie, Karras, Laine, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017), section 3.1.
+//   C(n, 1) = min(C_leaf(n), C_internal(n)),   C(n, i) = min(C_distribute(n, i), C(n, i - 1))
+//   C_leaf(n) = A(n) * c_leaf  if the subtree holds <= 8 primitives (ONE 8-wide triangle block, whatever its fill)
+//   C_internal(n) = C_distribute(n, 8) + A(n) * c_node,   C_distribute(n, j) = min_k C(left, k) + C(right, j - k)
+// `leaf_payload(first, count)` receives the primitive range [first, first + count) of the build's index array (subtree
+// ranges are contiguous in a top-down partition build) and returns the value stored in child[0].
+template <typename LeafFn>
+uint32_t CollapseToWideSAH(const std::vector<BinaryNode> &nodes, std::vector<rt::WNode> &out, uint32_t base, float c_node,
+                           float c_leaf, LeafFn &&leaf_payload);
+
 } // namespace RayB200
 
 // ---- template implementation ------------------------------------------------------------------------------------
@@ -125,6 +136,125 @@ uint32_t CollapseToWide(const std::vector<BinaryNode> &nodes, uint32_t node, std
         } // empty slots keep the zero box, like the reference (Core.cpp:849-853)
     }
     return base + my_index;
+}
+
+template <typename LeafFn>
+uint32_t CollapseToWideSAH(const std::vector<BinaryNode> &nodes, std::vector<rt::WNode> &out, uint32_t base,
+                           const float c_node, const float c_leaf, LeafFn &&leaf_payload) {
+    const uint32_t n = uint32_t(nodes.size());
+    struct Dp {
+        float c[8];       // c[i] = C(node, i), i = 1..7 (c[0] unused)
+        uint8_t split[9]; // split[j] = slots given to the left child by C_distribute(node, j), j = 2..8
+        uint8_t internal; // C(node, 1) is realised by an internal wide node (else a leaf)
+    };
+    std::vector<Dp> dp(n);
+    std::vector<uint32_t> sub_first(n), sub_count(n);
+    const float kInf = 3.402823466e+38F;
+    for (uint32_t i = n; i-- > 0;) { // children have larger indices than their parent: backwards = bottom-up
+        const BinaryNode &nd = nodes[i];
+        Dp &d = dp[i];
+        const float area = nd.box.half_area();
+        if (nd.count != 0) {
+            sub_first[i] = nd.first;
+            sub_count[i] = nd.count;
+            for (int k = 1; k < 8; ++k) {
+                d.c[k] = area * c_leaf;
+            }
+            d.internal = 0;
+            continue;
+        }
+        sub_first[i] = std::min(sub_first[nd.left], sub_first[nd.right]);
+        sub_count[i] = sub_count[nd.left] + sub_count[nd.right];
+        const Dp &l = dp[nd.left], &r = dp[nd.right];
+        float dist[9];
+        for (int j = 2; j <= 8; ++j) {
+            float best = kInf;
+            int best_k = 1;
+            for (int k = 1; k < j; ++k) {
+                if (k > 7 || j - k > 7) {
+                    continue;
+                }
+                const float c = l.c[k] + r.c[j - k];
+                if (c < best) {
+                    best = c;
+                    best_k = k;
+                }
+            }
+            dist[j] = best;
+            d.split[j] = uint8_t(best_k);
+        }
+        const float c_internal = dist[8] + area * c_node;
+        const float c_as_leaf = (sub_count[i] <= 8) ? area * c_leaf : kInf;
+        d.internal = (c_internal < c_as_leaf) ? 1 : 0;
+        d.c[1] = d.internal ? c_internal : c_as_leaf;
+        for (int j = 2; j < 8; ++j) {
+            d.c[j] = std::min(dist[j], d.c[j - 1]);
+        }
+    }
+    struct Emit {
+        const std::vector<BinaryNode> &nodes;
+        const std::vector<Dp> &dp;
+        const std::vector<uint32_t> &sub_first, &sub_count;
+        std::vector<rt::WNode> &out;
+        uint32_t base;
+        LeafFn &leaf_payload;
+        void collect(uint32_t node, int j, uint32_t *list, int &count) const {
+            const BinaryNode &nd = nodes[node];
+            if (j == 1 || nd.count != 0) {
+                list[count++] = node;
+                return;
+            }
+            const Dp &d = dp[node];
+            // C(node, j) = min(C_distribute(node, j), C(node, j - 1)): take fewer slots while that is as good
+            const float dist_j = dp[nd.left].c[d.split[j]] + dp[nd.right].c[j - d.split[j]];
+            if (j < 8 && !(dist_j <= d.c[j - 1])) {
+                collect(node, j - 1, list, count);
+                return;
+            }
+            collect(nd.left, d.split[j], list, count);
+            collect(nd.right, j - d.split[j], list, count);
+        }
+        uint32_t emit(uint32_t node) const {
+            const uint32_t my_index = uint32_t(out.size());
+            out.emplace_back();
+            std::memset(&out[my_index], 0, sizeof(rt::WNode));
+            const BinaryNode &nd = nodes[node];
+            if (nd.count != 0 || !dp[node].internal) {
+                rt::WNode &w = out[my_index];
+                for (int a = 0; a < 3; ++a) {
+                    w.bbox_min[a][0] = nd.box.mn[a];
+                    w.bbox_max[a][0] = nd.box.mx[a];
+                }
+                const uint32_t cnt = sub_count[node];
+                const uint32_t payload = leaf_payload(sub_first[node], cnt);
+                out[my_index].child[0] = rt::kLeafBit | payload;
+                out[my_index].child[1] = cnt;
+                return base + my_index;
+            }
+            uint32_t kids[8];
+            int nk = 0;
+            collect(nd.left, dp[node].split[8], kids, nk);
+            collect(nd.right, 8 - dp[node].split[8], kids, nk);
+            uint32_t child_ids[8];
+            for (int i = 0; i < 8; ++i) {
+                child_ids[i] = (i < nk) ? emit(kids[i]) : rt::kEmptyChild;
+            }
+            rt::WNode &w = out[my_index];
+            for (int i = 0; i < 8; ++i) {
+                w.child[i] = child_ids[i];
+                if (i < nk) {
+                    const Aabb &b = nodes[kids[i]].box;
+                    for (int a = 0; a < 3; ++a) {
+                        w.bbox_min[a][i] = b.mn[a];
+                        w.bbox_max[a][i] = b.mx[a];
+                    }
+                }
+            }
+            return base + my_index;
+        }
+    };
+    const Emit e{nodes, dp, sub_first, sub_count, out, base, leaf_payload};
+    return e.emit(0);
 }
 
 } // namespace RayB200

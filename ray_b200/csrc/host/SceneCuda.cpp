@@ -1,3 +1,4 @@
+#include <stdio.h>
 #include <stdlib.h>
 // SceneCuda.cpp -- see SceneCuda.h.  Behavioural spec: reference internal/SceneCPU.cpp (file:line cited per function).
 #include "SceneCuda.h"
@@ -511,20 +512,23 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
         return MeshHandle{};
     }
 
+    // binary SAH tree down to single triangles, then the SAH-optimal 8-wide collapse (BvhBuilder.h); RAY_HOST_BVH=greedy
+    // keeps the earlier build (binary leaves of <= 8 triangles, widest-area-first collapse) for A/B measurements
+    static const bool greedy = getenv("RAY_HOST_BVH") && !strcmp(getenv("RAY_HOST_BVH"), "greedy");
     std::vector<BinaryNode> bnodes;
     std::vector<uint32_t> order;
-    BuildBinaryBVH(boxes, 8, bnodes, order);
+    BuildBinaryBVH(boxes, greedy ? 8 : 1, bnodes, order);
 
     // every leaf owns one 8-triangle block; lanes past the leaf's count repeat its last triangle (Core.cpp:533-535)
     std::vector<rt::WNode> wide;
     wide.reserve(bnodes.size() / 4 + 8);
     const uint32_t node_base = uint32_t(wnodes_.size());
-    auto leaf_payload = [&](const BinaryNode &leaf) -> uint32_t {
+    auto leaf_range = [&](uint32_t first, uint32_t count) -> uint32_t {
         const uint32_t slot0 = uint32_t(tri_indices_.size());
         mtris_.emplace_back();
         rt::MTri &blk = mtris_.back();
         for (uint32_t k = 0; k < 8; ++k) {
-            const uint32_t src = order[leaf.first + std::min(k, leaf.count - 1)];
+            const uint32_t src = order[first + std::min(k, count - 1)];
             const TriRec &r = tris[src];
             tri_indices_.push_back(tri_base + r.tri);
             for (int c = 0; c < 4; ++c) {
@@ -535,7 +539,14 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
         }
         return slot0;
     };
-    const uint32_t root = CollapseToWide(bnodes, 0, wide, node_base, leaf_payload);
+    auto leaf_payload = [&](const BinaryNode &leaf) -> uint32_t { return leaf_range(leaf.first, leaf.count); };
+    float c_node = 1.0f, c_leaf = 1.6f;
+    if (const char *e = getenv("RAY_HOST_BVH_COST")) {
+        sscanf(e, "%f,%f", &c_node, &c_leaf);
+    }
+    const uint32_t root = greedy ? CollapseToWide(bnodes, 0, wide, node_base, leaf_payload)
+                                 : CollapseToWideSAH(bnodes, wide, node_base, c_node, c_leaf, leaf_range);
+    (void)root;
     wnodes_.insert(wnodes_.end(), wide.begin(), wide.end());
     blas_nodes_end_ = uint32_t(wnodes_.size());
 
