@@ -21,6 +21,7 @@ ap.add_argument("--spp", type=int, default=8)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--no-sort", action="store_true")
 ap.add_argument("--scene", default="hall")
+ap.add_argument("--max-total-depth", type=int, default=0)
 args = ap.parse_args()
 
 t0 = time.time()
@@ -30,6 +31,8 @@ elif args.scene == "cornell":
     desc = scenes.cornell_box(args.w, args.h)
 else:
     desc = scenes.instanced(1000, 10000, args.w, args.h)
+if args.max_total_depth:
+    desc.camera.max_total_depth = args.max_total_depth
 pair = Pair(oracle, desc)
 print(f"scene {desc.name}: {desc.triangle_count()} tris, wnodes {pair.view.wnodes.count}, build {time.time()-t0:.1f}s", flush=True)
 flags = capi.RC_RENDER_ASYNC | (capi.RC_RENDER_NO_SORT if args.no_sort else 0)
