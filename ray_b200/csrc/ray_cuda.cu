@@ -954,6 +954,7 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
     patched.lights.ptr = lts.data();
     sv = &patched;
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_scene = false; // a failed upload must not leave a half-replaced scene renderable
     if (upload_array(ctx, ctx->wnodes, sv->wnodes, sizeof(WNode), "wnodes") ||
         upload_array(ctx, ctx->mtris, sv->mtris, sizeof(MTri), "mtris") ||
         upload_array(ctx, ctx->tri_indices, sv->tri_indices, 4, "tri_indices") ||
