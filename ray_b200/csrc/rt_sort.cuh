@@ -4,10 +4,10 @@
 // The step is results-neutral: every pixel owns at most one ray per bounce and each ray carries its pixel in `xy`, so
 // the ORDER of the ray list never reaches the image.  What matters is that rays that
 // start close together and point the same way sit next to each other so a warp walks the same BVH nodes.  So instead of
-// reproducing the reference's 32-bit hash + full radix sort (~240 B/ray), this is ONE counting-sort pass over a
-// 15-bit key = direction octant (3 bits, major) | 12-bit Morton code of the origin in a 16^3 grid over the scene bounds:
-//   k_sort_hist    read o,d (32 B) -> key (4 B) + global histogram (32768 bins, L2-resident atomics)
-//   k_sort_scan    one block: exclusive scan of the histogram
+// reproducing the reference's 32-bit hash + full radix sort (~240 B/ray), this is ONE counting-sort pass over an
+// 18-bit key = direction cell (6 bits, 8x8 octahedral, major) | 12-bit Morton code of the origin in a 16^3 grid:
+//   k_sort_hist    read o,d (32 B) -> key (4 B) + global histogram (262144 bins, L2-resident atomics)
+//   k_sort_scan    one block per 32768 bins: exclusive scan of the histogram chunk + chunk total
 //   k_sort_scatter read ray (72 B + key) -> slot = atomicAdd(bin) -> write ray (72 B)
 // ~= 184 B/ray of HBM traffic, no multi-pass key shuffling.  Order inside a bin is arbitrary (and irrelevant).
 #pragma once
@@ -20,6 +20,7 @@ struct SortBufs {
     uint32_t *keys = nullptr;        // key per input ray
     uint32_t *keys_sorted = nullptr; // key per output ray (diagnostics / stage API)
     uint32_t *hist = nullptr;        // kMaxBounces x kSortBins: one histogram per ray list, zeroed once per sample
+    uint32_t *chunk_totals = nullptr; // kMaxBounces x kSortChunks (k_sort_scan -> k_sort_scatter)
     float root_min[3] = {0, 0, 0};
     float inv_cell[3] = {1, 1, 1};
 };
@@ -29,6 +30,9 @@ inline int alloc_sort_bufs(SortBufs &s, size_t n) {
     cudaFree(s.keys_sorted);
     s.keys = s.keys_sorted = nullptr;
     if (!s.hist && cudaMalloc(&s.hist, size_t(kMaxBounces) * kSortBins * sizeof(uint32_t)) != cudaSuccess) {
+        return 1;
+    }
+    if (!s.chunk_totals && cudaMalloc(&s.chunk_totals, size_t(kMaxBounces) * 64 * sizeof(uint32_t)) != cudaSuccess) {
         return 1;
     }
     if (n == 0) {
@@ -45,6 +49,7 @@ inline void free_sort_bufs(SortBufs &s) {
     cudaFree(s.keys);
     cudaFree(s.keys_sorted);
     cudaFree(s.hist);
+    cudaFree(s.chunk_totals);
     s = SortBufs{};
 }
 
@@ -66,68 +71,77 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *counters, int
     }
 }
 
-// exclusive scan of kSortBins counters by one 1024-thread block, 32768 bins per round.  Warp w owns bins
-// [1024 w, 1024 (w+1)) of the round as 32 rows of 32: every load and store is a coalesced 128-byte row, the scan inside
-// a row is a shuffle scan.
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *hist) {
-    static_assert(kSortBins % (32 * 1024) == 0, "whole rounds");
+// Exclusive scan of kSortBins counters: one 1024-thread block per 32768-bin chunk, all chunks in parallel.  Each block
+// scans its chunk locally (warp w owns bins [1024 w, 1024 (w+1)) of the chunk as 32 rows of 32: coalesced rows, shuffle
+// scan inside a row) and publishes the chunk's total in chunk_totals[]; the scatter kernel adds the prefix of the totals
+// of the chunks before the key's chunk, so no second pass and no inter-block wait is needed.
+constexpr int kSortChunkBins = 32 * 1024;
+constexpr int kSortChunks = kSortBins / kSortChunkBins;
+static_assert(kSortBins % kSortChunkBins == 0 && kSortChunks <= 64, "whole chunks");
+
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *hist, uint32_t *chunk_totals) {
     __shared__ uint32_t warp_sums[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t carry = 0;
-    for (int round = 0; round < kSortBins / (32 * 1024); ++round) {
-        uint32_t *row0 = hist + round * (32 * 1024) + warp * 1024 + lane;
-        uint32_t excl[32];
-        uint32_t running = 0;
+    uint32_t *row0 = hist + blockIdx.x * kSortChunkBins + warp * 1024 + lane;
+    uint32_t excl[32];
+    uint32_t running = 0;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const uint32_t v = row0[r * 32];
-            uint32_t incl = v;
+    for (int r = 0; r < 32; ++r) {
+        const uint32_t v = row0[r * 32];
+        uint32_t incl = v;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) {
-                    incl += u;
-                }
-            }
-            excl[r] = running + incl - v;
-            running += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) {
-            warp_sums[warp] = running;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t t = warp_sums[lane];
-            uint32_t w = t;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, w, off);
-                if (lane >= off) {
-                    w += u;
-                }
-            }
-            warp_sums[lane] = w - t;
-            if (lane == 31) {
-                warp_sums[32] = w; // total of this round
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) {
+                incl += u;
             }
         }
-        __syncthreads();
-        const uint32_t base = carry + warp_sums[warp];
-        carry += warp_sums[32];
+        excl[r] = running + incl - v;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        warp_sums[warp] = running;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t t = warp_sums[lane];
+        uint32_t w = t;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            row0[r * 32] = base + excl[r];
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) {
+                w += u;
+            }
         }
-        __syncthreads();
+        warp_sums[lane] = w - t;
+        if (lane == 31) {
+            chunk_totals[blockIdx.x] = w;
+        }
+    }
+    __syncthreads();
+    const uint32_t base = warp_sums[warp];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        row0[r * 32] = base + excl[r];
     }
 }
 
 __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t *counters, int bounce, RayBuf src, RayBuf dst,
-                                                      const uint32_t *keys, uint32_t *offsets, uint32_t *keys_sorted) {
+                                                      const uint32_t *keys, uint32_t *offsets,
+                                                      const uint32_t *chunk_totals, uint32_t *keys_sorted) {
+    __shared__ uint32_t chunk_base[kSortChunks];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < kSortChunks; ++c) {
+            chunk_base[c] = acc;
+            acc += chunk_totals[c];
+        }
+    }
+    __syncthreads();
     const uint32_t count = counters[CNT_RAYS + bounce];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t key = keys[i];
-        const uint32_t slot = atomicAdd(&offsets[key], 1u);
+        const uint32_t slot = chunk_base[key / kSortChunkBins] + atomicAdd(&offsets[key], 1u);
         dst.o_cw[slot] = src.o_cw[i];
         dst.d_cs[slot] = src.d_cs[i];
         dst.c_pdf[slot] = src.c_pdf[i];
@@ -150,8 +164,9 @@ inline void sort_rays(SortBufs &s, const KParams &p, const RayBuf &src, const Ra
         cudaMemsetAsync(hist, 0, kSortBins * sizeof(uint32_t), stream);
         k_sort_hist<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, g, s.keys, hist);
     }
-    k_sort_scan<<<1, 1024, 0, stream>>>(hist);
-    k_sort_scatter<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, dst, s.keys, hist,
+    uint32_t *chunk_totals = s.chunk_totals + size_t(bounce) * kSortChunks;
+    k_sort_scan<<<kSortChunks, 1024, 0, stream>>>(hist, chunk_totals);
+    k_sort_scatter<<<num_sms * 8, 256, 0, stream>>>(p.counters, bounce, src, dst, s.keys, hist, chunk_totals,
                                                     want_sorted_keys ? s.keys_sorted : nullptr);
 }
 
