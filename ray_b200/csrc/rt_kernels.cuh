@@ -110,7 +110,7 @@ RT_DEV uint32_t ray_sort_key(float4 o, float4 d, const SortGrid &g) {
     const uint32_t oct = uint32_t(qy * dres + qx);
 #endif
 #if defined(RT_SORT_ORIGIN_MAJOR) && RT_SORT_ORIGIN_MAJOR
-    return (morton << 3) | oct;
+    return (morton << kSortDirBits) | oct;
 #else
     return (oct << (3 * kSortCellBits)) | morton;
 #endif
