@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "rt_kernels.cuh"
+#include "rt_trace.cuh"
 #include "rt_sort.cuh"
 #include "rt_denoise.cuh"
 
@@ -63,6 +64,10 @@ struct rc_ctx {
     DevArray wnodes, mtris, tri_indices, tri_materials, materials, mesh_instances, vertices, vtx_indices, lights,
         light_cwnodes;
     DevArray tex_descs, tex_texels, qtree;
+    DevArray dnodes, blas_roots, dmtris; // device-built traversal copies (rt_trace.cuh)
+    uint32_t tlas_root_word = kEmptyChild;
+    uint32_t *d_build_flag = nullptr;
+    int trace_fin_min = 32;         // lanes of a warp that must have finished before their epilogue + refill is issued
     float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
     size_t nlm_scratch_elems = 0;
     float last_inv_gamma = 1.0f, last_variance_threshold = 0.0f; // tonemap_params_ / variance_threshold_ of the reference
@@ -215,6 +220,10 @@ int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
 
     memset(&p, 0, sizeof(p));
     p.sc.geo.nodes = static_cast<const WNode *>(ctx->wnodes.ptr);
+    p.sc.geo.dnodes = static_cast<const WNode *>(ctx->dnodes.ptr);
+    p.sc.geo.blas_roots = static_cast<const uint32_t *>(ctx->blas_roots.ptr);
+    p.sc.geo.dmtris = ctx->dmtris.ptr;
+    p.sc.geo.tlas_root_word = ctx->tlas_root_word;
     p.sc.geo.mtris = static_cast<const MTri *>(ctx->mtris.ptr);
     p.sc.geo.tri_indices = static_cast<const uint32_t *>(ctx->tri_indices.ptr);
     p.sc.geo.tri_materials = static_cast<const TriMat *>(ctx->tri_materials.ptr);
@@ -285,6 +294,72 @@ int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     p.rect_h = r.h;
     p.iteration = pass->iteration;
     p.rand_seed = host_hash(uint32_t((pass->iteration - 1) / kRandSamples));
+    return 0;
+}
+
+// device-side copies the trace kernels walk (rt_trace.cuh): nodes with resolved child words + unhittable empty slots,
+// BLAS root word per instance, TLAS root word
+int build_traversal_copies(rc_ctx *ctx, const rc_scene_view *sv) {
+    const uint32_t n_nodes = sv->wnodes.count, n_inst = sv->mesh_instances.count;
+    const uint32_t n_blocks = sv->mtris.count;
+    for (DevArray *a : {&ctx->dnodes, &ctx->blas_roots, &ctx->dmtris}) {
+        const size_t want = (a == &ctx->dnodes) ? size_t(n_nodes) * sizeof(WNode)
+                                                : (a == &ctx->dmtris ? size_t(n_blocks) * sizeof(MTri) : size_t(n_inst) * 4);
+        if (!(a->ptr && want != 0 && a->bytes == want)) {
+            if (a->ptr) {
+                cudaFree(a->ptr);
+                *a = DevArray{};
+            }
+            CU_CHECK(ctx, cudaMalloc(&a->ptr, want ? want : 256));
+        }
+        a->bytes = want;
+    }
+    ctx->dnodes.count = n_nodes;
+    ctx->blas_roots.count = n_inst;
+    ctx->dmtris.count = n_blocks;
+    if (n_blocks != 0) {
+        k_build_dmtris<<<(n_blocks * 4 + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const MTri *>(ctx->mtris.ptr),
+                                                                          static_cast<float4 *>(ctx->dmtris.ptr), n_blocks);
+    }
+    ctx->tlas_root_word = kEmptyChild;
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_build_flag, 0, sizeof(uint32_t), ctx->stream));
+    if (n_nodes != 0) {
+        k_build_dnodes<<<(n_nodes * 8 + 255) / 256, 256, 0, ctx->stream>>>(
+            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<WNode *>(ctx->dnodes.ptr), n_nodes, ctx->d_build_flag);
+    }
+    if (n_inst != 0) {
+        k_build_blas_roots<<<(n_inst + 255) / 256, 256, 0, ctx->stream>>>(
+            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<const MeshInstance *>(ctx->mesh_instances.ptr), n_inst,
+            n_nodes, static_cast<uint32_t *>(ctx->blas_roots.ptr), ctx->d_build_flag);
+    }
+    uint32_t flag = 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(&flag, ctx->d_build_flag, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    if (flag == 1) {
+        return fail(ctx, "rc_upload_scene: a BVH leaf cannot be encoded (first primitive >= 2^27 - 1 or more than 128 triangles)");
+    }
+    if (flag == 2) {
+        return fail(ctx, "rc_upload_scene: a BVH child box has min > max");
+    }
+    if (sv->tlas_root != 0xffffffffu) {
+        if (sv->tlas_root >= n_nodes) {
+            return fail(ctx, "rc_upload_scene: tlas_root %u outside the node array (%u)", sv->tlas_root, n_nodes);
+        }
+        // the root may itself be a leaf (a scene with one instance): read its two words from the caller's array
+        const WNode *host_nodes = static_cast<const WNode *>(sv->wnodes.ptr);
+        const uint32_t c0 = host_nodes[sv->tlas_root].child[0], c1 = host_nodes[sv->tlas_root].child[1];
+        if (c0 & kLeafBit) {
+            const uint32_t first = c0 & kPrimIndexBits;
+            const uint32_t blocks = ((first & 7u) + c1 + 7u) / 8u;
+            if (first >= kLeafFirstBits || blocks == 0 || blocks > 16) {
+                return fail(ctx, "rc_upload_scene: the TLAS root leaf cannot be encoded");
+            }
+            ctx->tlas_root_word = kLeafBit | ((blocks - 1u) << kLeafBlocksShift) | first;
+        } else {
+            ctx->tlas_root_word = sv->tlas_root;
+        }
+    }
     return 0;
 }
 
@@ -388,7 +463,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     const bool have_geo = ctx->scene_info.tlas_root != 0xffffffffu;
 
     if (have_geo) {
-        k_trace_closest<false, false><<<trace_grid, 128, 0, s>>>(p, ctx->rays[0], ctx->hits, 0);
+        k_trace_closest<false, false><<<trace_grid, kTraceThreads, 0, s>>>(p, ctx->rays[0], ctx->hits, 0, ctx->trace_fin_min);
         ctx->kernel_launches[KF_TRACE]++;
     }
     record(ctx, EV_PTRACE);
@@ -402,7 +477,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     record(ctx, EV_PSHADE);
 
     if (have_geo) {
-        k_trace_shadow<<<trace_grid, 128, 0, s>>>(p, ctx->shadow, 0, clamp_limit(p.ps.clamp_direct));
+        k_trace_shadow<<<trace_grid, kTraceThreads, 0, s>>>(p, ctx->shadow, 0, clamp_limit(p.ps.clamp_direct), ctx->trace_fin_min);
         ctx->kernel_launches[KF_SHADOW]++;
     }
     record(ctx, EV_PSHADOW);
@@ -419,9 +494,9 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
         record(ctx, e + 0);
         if (have_geo) {
             if (ctx->scene_info.visible_lights_count != 0) {
-                k_trace_closest<true, true><<<trace_grid, 128, 0, s>>>(p, ctx->rays[cur], ctx->hits, bounce);
+                k_trace_closest<true, true><<<trace_grid, kTraceThreads, 0, s>>>(p, ctx->rays[cur], ctx->hits, bounce, ctx->trace_fin_min);
             } else {
-                k_trace_closest<false, true><<<trace_grid, 128, 0, s>>>(p, ctx->rays[cur], ctx->hits, bounce);
+                k_trace_closest<false, true><<<trace_grid, kTraceThreads, 0, s>>>(p, ctx->rays[cur], ctx->hits, bounce, ctx->trace_fin_min);
             }
         } else {
             k_init_hits<<<shade_grid, 128, 0, s>>>(p, ctx->hits, bounce);
@@ -436,7 +511,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
         }
         record(ctx, e + 2);
         if (have_geo) {
-            k_trace_shadow<<<trace_grid, 128, 0, s>>>(p, ctx->shadow, bounce, clamp_limit(p.ps.clamp_indirect));
+            k_trace_shadow<<<trace_grid, kTraceThreads, 0, s>>>(p, ctx->shadow, bounce, clamp_limit(p.ps.clamp_indirect), ctx->trace_fin_min);
             ctx->kernel_launches[KF_SHADOW]++;
         }
         record(ctx, e + 3);
@@ -637,11 +712,24 @@ int rc_create(int device, rc_ctx **out_ctx) {
             return 6;
         }
     }
-    // traversal stacks live in local memory: give L1 the whole carve-out
-    cudaFuncSetAttribute(k_trace_closest<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace_closest<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace_shadow, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    // the trace kernels keep their stacks in static shared memory (rt_trace.cuh): RT_TRACE_BLOCKS blocks must fit, the
+    // rest of the unified array stays L1
+    {
+        const int pct = int((sizeof(TraceSmem) + 1024) * RT_TRACE_BLOCKS * 100 / (228 * 1024)) + 1;
+        const int carve = pct > 100 ? 100 : pct;
+        cudaFuncSetAttribute(k_trace_closest<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_trace_closest<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_trace_closest<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_trace_shadow, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+    if (const char *e = getenv("RC_TRACE_FIN_MIN")) { // development knob
+        ctx->trace_fin_min = atoi(e);
+    }
+    if (cudaMalloc(&ctx->d_build_flag, sizeof(uint32_t)) != cudaSuccess) {
+        rc_destroy(ctx);
+        return 6;
+    }
     cudaFuncSetAttribute(k_shade<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_shade<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_shade<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -686,7 +774,8 @@ void rc_destroy(rc_ctx *ctx) {
     cudaFree(ctx->d_filter_table);
     cudaFree(ctx->d_srgb_lut);
     cudaFree(ctx->nlm_scratch);
-    for (DevArray *a : {&ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
+    cudaFree(ctx->d_build_flag);
+    for (DevArray *a : {&ctx->dnodes, &ctx->blas_roots, &ctx->dmtris, &ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
                         &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {
         cudaFree(a->ptr);
@@ -987,6 +1076,9 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
     }
     ctx->li_count = sv->li_indices.count;
     set_sort_bounds(ctx->sort, sv->bounds_min, sv->bounds_max);
+    if (build_traversal_copies(ctx, sv)) {
+        return 1;
+    }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_scene = true;
     return 0;
@@ -1226,9 +1318,9 @@ int rc_stage_trace_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays, void 
     const int grid = persistent_grid(ctx, RT_TRACE_BLOCKS);
     if (ctx->scene_info.tlas_root != 0xffffffffu) {
         if (trace_lights && ctx->scene_info.visible_lights_count != 0) {
-            k_trace_closest<true, false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0);
+            k_trace_closest<true, false><<<grid, kTraceThreads, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0, ctx->trace_fin_min);
         } else {
-            k_trace_closest<false, false><<<grid, 128, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0);
+            k_trace_closest<false, false><<<grid, kTraceThreads, 0, ctx->stream>>>(p, ctx->rays[0], ctx->hits, 0, ctx->trace_fin_min);
         }
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1312,7 +1404,7 @@ int rc_stage_trace_shadow_rays(rc_ctx *ctx, const rc_pass_desc *pass, const void
         return 1;
     }
     if (ctx->scene_info.tlas_root != 0xffffffffu) {
-        k_trace_shadow<<<persistent_grid(ctx, RT_TRACE_BLOCKS), 128, 0, ctx->stream>>>(p, ctx->shadow, 0, clamp_limit(clamp_val));
+        k_trace_shadow<<<persistent_grid(ctx, RT_TRACE_BLOCKS), kTraceThreads, 0, ctx->stream>>>(p, ctx->shadow, 0, clamp_limit(clamp_val), ctx->trace_fin_min);
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaGetLastError());

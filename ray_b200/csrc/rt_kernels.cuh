@@ -17,7 +17,7 @@
 //  * k_shade is instruction-FETCH bound (177 KB of straight-line SASS walked once per ray, I-cache hit rate 65 %):
 //    big blocks whose warps are re-aligned with __syncthreads() between the phases walk the same cache lines together
 //    (119 -> 82 ms per 16 samples); 64 registers / thread costs spills but doubles the resident warps.
-//  * the trace kernels want 6 resident 128-thread blocks (80 registers): 96 -> 88 ms closest, 102 -> 89 ms shadow.
+//  * the trace kernels (rt_trace.cuh) run RT_TRACE_BLOCKS resident 128-thread blocks per SM.
 #ifndef RT_SHADE_THREADS
 #define RT_SHADE_THREADS 512
 #endif
@@ -332,182 +332,6 @@ __global__ void __launch_bounds__(256) k_raygen(KParams p, RayBuf rays, HitBuf h
     }
 }
 
-// Work distribution of the persistent trace kernels.  A warp takes `pk` consecutive rays at a time: 32 when the list
-// is long, fewer when the list has less than 32 rays per resident warp (deep bounces), because the rays of a packet that
-// diverge are serialised and a short list is better spread thin over all warps.  The first packet of every warp is
-// static (no atomic); later ones come from the list's queue head, which therefore counts from 0 past the static part.
-struct PacketQueue {
-    uint32_t count, pk, static_end, next;
-    bool first;
-};
-
-RT_DEV PacketQueue packet_queue_init(uint32_t count) {
-    PacketQueue q;
-    q.count = count;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t pk = 32;
-    while (pk > 4 && uint64_t(pk / 2) * warps >= count) {
-        pk >>= 1;
-    }
-    q.pk = pk;
-    q.static_end = warps * pk;
-    q.next = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * pk;
-    q.first = true;
-    return q;
-}
-
-// returns false when the list is exhausted; else `base` = first ray of this warp's packet
-RT_DEV bool packet_queue_next(PacketQueue &q, uint32_t *head, int lane, uint32_t &base) {
-    if (q.first) {
-        q.first = false;
-        base = q.next;
-    } else {
-        uint32_t b = 0;
-        if (lane == 0) {
-            b = atomicAdd(head, q.pk);
-        }
-        base = q.static_end + __shfl_sync(0xffffffffu, b, 0);
-    }
-    return base < q.count;
-}
-
-// ---- TraceRays: IntersectScene (CoreRef.cpp:3041-3158) [+ IntersectAreaLights :3616-3860] ------------------------
-// Persistent warps pull 32-ray packets from a queue head; `bounce` selects the counter slot.
-// INIT_HITS: secondary lists start from the default "no intersection" record (RendererCPU.h:532-535) built in
-// registers instead of a memset pass + 20 B/ray read.
-template <bool TRACE_LIGHTS, bool INIT_HITS>
-__global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_closest(KParams p, RayBuf rays, HitBuf hits, int bounce) {
-    const uint32_t count = p.counters[CNT_RAYS + bounce];
-    uint32_t *head = &p.counters[CNT_HEAD_TRACE + bounce];
-    const int lane = threadIdx.x & 31;
-    TraverseCounters cnt{0, 0};
-    StackEntry st[2 * kMaxStack];
-    PacketQueue q = packet_queue_init(count);
-    uint32_t base;
-    while (packet_queue_next(q, head, lane, base)) {
-        const uint32_t i = base + lane;
-        if (lane < q.pk && i < count) {
-            const float4 a = rays.o_cw[i], dd = rays.d_cs[i];
-            const uint2 xd = rays.xy_depth[i];
-            const v3 r_o = v3{a.x, a.y, a.z};
-            const v3 rd = v3{dd.x, dd.y, dd.z};
-            v3 ro = r_o;
-            uint32_t depth = xd.y;
-            Hit inter;
-            if (INIT_HITS) {
-                inter.obj = -1;
-                inter.prim = -1;
-                inter.t = kMaxDist;
-                inter.u = 0.0f;
-                inter.v = -1.0f;
-            } else {
-                inter = load_hit(hits, i);
-            }
-            const uint32_t ray_flags = (1u << ray_type(depth));
-            bool ray_dirty = false;
-            v3 rc;
-            uint32_t rand_dim = kRandDimBase + total_depth(depth) * kRandDimBounce;
-            while (true) {
-                const float t_val = inter.t;
-                const bool hit_found = traverse_scene<false>(p.sc.geo, ro, rd, ray_flags, inter, st, cnt);
-                if (!hit_found) {
-                    break;
-                }
-                const bool is_backfacing = (inter.prim < 0);
-                const uint32_t tri_index = is_backfacing ? uint32_t(-inter.prim - 1) : uint32_t(inter.prim);
-                const TriMat tm = p.sc.geo.tri_materials[tri_index];
-                if ((!is_backfacing && (tm.front_mi & kMatSolidBit)) || (is_backfacing && (tm.back_mi & kMatSolidBit))) {
-                    break; // solid hit
-                }
-                const Material *mat = is_backfacing ? &p.sc.surf.materials[tm.back_mi & kMatIndexBits]
-                                                    : &p.sc.surf.materials[tm.front_mi & kMatIndexBits];
-                const uint32_t px_hash = hash_u32(xd.x);
-                const uint32_t rand_hash = hash_combine(px_hash, p.rand_seed);
-                const v2 mix_term_rand = rand2d(rand_dim + kRandDimBsdfPick, rand_hash, p.iteration - 1, p.sc.rand_seq);
-                float trans_r = mix_term_rand.x;
-                // alpha-textured Mix nodes (CoreRef.cpp:3088-3115): uvs at the hit + the bounce's texture jitter
-                v2 uvs = v2{0.0f, 0.0f}, tex_rand = v2{0.0f, 0.0f};
-                if (p.sc.tex.descs != nullptr && mat->type == NODE_MIX) {
-                    const Vertex &v1 = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 0]];
-                    const Vertex &v2_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 1]];
-                    const Vertex &v3_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 2]];
-                    const float w = 1.0f - inter.u - inter.v;
-                    uvs = v2{v1.t[0] * w + v2_.t[0] * inter.u + v3_.t[0] * inter.v,
-                             v1.t[1] * w + v2_.t[1] * inter.u + v3_.t[1] * inter.v};
-                    tex_rand = rand2d(rand_dim + kRandDimTex, rand_hash, p.iteration - 1, p.sc.rand_seq);
-                }
-                while (mat->type == NODE_MIX) {
-                    float mix_val = mat->tangent_rotation_or_strength;
-                    const uint32_t mix_texture = mat->textures[kTexBase];
-                    if (mix_texture != kTexInvalid) {
-                        mix_val *= tex_sample_color(p.sc.tex, mix_texture, uvs, 0, tex_rand).x;
-                    }
-                    if (trans_r > mix_val) {
-                        mat = &p.sc.surf.materials[mat->textures[kMixMat1]];
-                        trans_r = safe_div_pos(trans_r - mix_val, 1.0f - mix_val);
-                    } else {
-                        mat = &p.sc.surf.materials[mat->textures[kMixMat2]];
-                        trans_r = safe_div_pos(trans_r, mix_val);
-                    }
-                }
-                if (mat->type != NODE_TRANSPARENT) {
-                    break;
-                }
-                if (!ray_dirty) {
-                    const float4 c = rays.c_pdf[i];
-                    rc = v3{c.x, c.y, c.z};
-                    ray_dirty = true;
-                }
-                const bool can_terminate_path = transp_depth(depth) > p.ps.min_transp_depth;
-                const float lum_ = fmaxf(rc.x, fmaxf(rc.y, rc.z));
-                const float pr = mix_term_rand.y;
-                const float q = can_terminate_path ? fmaxf(0.05f, 1.0f - lum_) : 0.0f;
-                if (pr < q || lum_ == 0.0f || transp_depth(depth) + 1 >= p.ps.max_transp_depth) {
-                    rc = v3{0.0f, 0.0f, 0.0f};
-                    break;
-                }
-                rc.x *= mat->base_color[0] / (1.0f - q);
-                rc.y *= mat->base_color[1] / (1.0f - q);
-                rc.z *= mat->base_color[2] / (1.0f - q);
-                const float t = inter.t + kHitBias;
-                ro = ro + rd * t;
-                inter.v = -1.0f;
-                inter.t = t_val - inter.t;
-                depth += pack_depth(0, 0, 0, 1);
-                rand_dim += kRandDimBounce;
-            }
-            inter.t += length(r_o - ro);
-            if (TRACE_LIGHTS) {
-                if (p.sc.lights.visible_lights_count != 0) {
-                    // the light-tree stack is not live at the same time as the BVH stack: reuse the storage
-                    intersect_area_lights(p.sc.lights, r_o, rd, (1u << ray_type(depth)), inter,
-                                          reinterpret_cast<LightStackEntry *>(st));
-                }
-            }
-            store_hit(hits, i, inter);
-            if (ray_dirty) {
-                float4 c = rays.c_pdf[i];
-                c.x = rc.x;
-                c.y = rc.y;
-                c.z = rc.z;
-                rays.c_pdf[i] = c;
-                rays.xy_depth[i] = make_uint2(xd.x, depth);
-            }
-        }
-    }
-    // one 64-bit atomic per warp for the traversal statistics
-    uint32_t n = cnt.nodes, l = cnt.leaves;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        n += __shfl_xor_sync(0xffffffffu, n, off);
-        l += __shfl_xor_sync(0xffffffffu, l, off);
-    }
-    if (lane == 0 && (n | l)) {
-        atomicAdd(&p.totals[TOT_NODES], (unsigned long long)n);
-        atomicAdd(&p.totals[TOT_LEAVES], (unsigned long long)l);
-    }
-}
-
 // ---- ShadePrimary / ShadeSecondary (ShadeRef.cpp:1654-1737) --------------------------------------------------------
 // `bounce` = index of the ray list being shaded (0 = primary).  Secondary rays go to list bounce+1.
 template <bool PRIMARY, bool TEX>
@@ -609,117 +433,6 @@ __global__ void k_init_hits(KParams p, HitBuf hits, int bounce) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         hits.tuvp[i] = make_float4(kMaxDist, 0.0f, -1.0f, __int_as_float(-1));
         hits.obj[i] = -1;
-    }
-}
-
-// ---- TraceShadowRays (CoreRef.cpp:4856-4882) + IntersectScene(shadow) (:3160-3262) -------------------------------
-__global__ void __launch_bounds__(128, RT_TRACE_BLOCKS) k_trace_shadow(KParams p, ShadowBuf srays, int stage, float limit) {
-    const uint32_t count = p.counters[CNT_SHADOW + stage];
-    uint32_t *head = &p.counters[CNT_HEAD_SHADOW + stage];
-    const int lane = threadIdx.x & 31;
-    TraverseCounters cnt{0, 0};
-    StackEntry st[2 * kMaxStack];
-    PacketQueue q = packet_queue_init(count);
-    uint32_t base;
-    while (packet_queue_next(q, head, lane, base)) {
-        const uint32_t i = base + lane;
-        if (lane < q.pk && i < count) {
-            const ShadowRayD r = load_shadow(srays, i);
-            const v3 rd = r.d;
-            v3 ro = r.o;
-            v3 rc = r.c;
-            int depth = transp_depth(r.depth);
-            uint32_t rand_dim = kRandDimBase + total_depth(r.depth) * kRandDimBounce;
-            float dist = r.dist > 0.0f ? r.dist : kMaxDist;
-            while (dist > kHitBias) {
-                Hit inter;
-                inter.obj = -1;
-                inter.prim = -1;
-                inter.t = dist;
-                inter.u = 0.0f;
-                inter.v = -1.0f;
-                const bool solid_hit = traverse_scene<true>(p.sc.geo, ro, rd, (1u << RAY_SHADOW), inter, st, cnt);
-                if (solid_hit || depth > p.ps.max_transp_depth) {
-                    rc = v3{0.0f, 0.0f, 0.0f};
-                }
-                if (solid_hit || depth > p.ps.max_transp_depth || inter.v < 0.0f) {
-                    break;
-                }
-                const bool is_backfacing = (inter.prim < 0);
-                const uint32_t tri_index = is_backfacing ? uint32_t(-inter.prim - 1) : uint32_t(inter.prim);
-                const TriMat tm = p.sc.geo.tri_materials[tri_index];
-                const uint32_t mat_index = is_backfacing ? (tm.back_mi & kMatIndexBits) : (tm.front_mi & kMatIndexBits);
-                // transparency throughput of the (possibly mixed) material, ShadeRef-independent small stack
-                uint32_t mstack[16];
-                float wstack[16];
-                int ms = 0;
-                mstack[ms] = mat_index;
-                wstack[ms++] = 1.0f;
-                v3 throughput = v3{0.0f, 0.0f, 0.0f};
-                // alpha-textured Mix nodes (CoreRef.cpp:3203-3240)
-                v2 sh_uvs = v2{0.0f, 0.0f}, tex_rand = v2{0.0f, 0.0f};
-                if (p.sc.tex.descs != nullptr) {
-                    const Vertex &v1 = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 0]];
-                    const Vertex &v2_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 1]];
-                    const Vertex &v3_ = p.sc.surf.vertices[p.sc.surf.vtx_indices[tri_index * 3 + 2]];
-                    const float w = 1.0f - inter.u - inter.v;
-                    sh_uvs = v2{v1.t[0] * w + v2_.t[0] * inter.u + v3_.t[0] * inter.v,
-                                v1.t[1] * w + v2_.t[1] * inter.u + v3_.t[1] * inter.v};
-                    tex_rand = rand2d(rand_dim + kRandDimTex, hash_combine(hash_u32(r.xy), p.rand_seed), p.iteration - 1,
-                                      p.sc.rand_seq);
-                }
-                while (ms--) {
-                    const Material *mat = &p.sc.surf.materials[mstack[ms]];
-                    const float weight = wstack[ms];
-                    if (mat->type == NODE_MIX) {
-                        float mix_val = mat->tangent_rotation_or_strength;
-                        const uint32_t mix_texture = mat->textures[kTexBase];
-                        if (mix_texture != kTexInvalid) {
-                            mix_val *= tex_sample_color(p.sc.tex, mix_texture, sh_uvs, 0, tex_rand).x;
-                        }
-                        mstack[ms] = mat->textures[kMixMat1];
-                        wstack[ms++] = weight * (1.0f - mix_val);
-                        mstack[ms] = mat->textures[kMixMat2];
-                        wstack[ms++] = weight * mix_val;
-                    } else if (mat->type == NODE_TRANSPARENT) {
-                        throughput += weight * mk3(mat->base_color);
-                    }
-                }
-                rc *= throughput;
-                if (lum(rc) < kFltEps) {
-                    break;
-                }
-                const float t = inter.t + kHitBias;
-                ro = ro + rd * t;
-                dist -= t;
-                ++depth;
-                rand_dim += kRandDimBounce;
-            }
-            if (p.sc.lights.blocker_lights_count != 0) {
-                rc *= intersect_area_lights_shadow(p.sc.lights, r.o, r.d, r.dist, st);
-            }
-            const float sum = ((rc.x + rc.y) + rc.z) + 0.0f;
-            if (sum > limit) {
-                rc *= (limit / sum);
-            }
-            const int x = int((r.xy >> 16) & 0xffff), y = int(r.xy & 0xffff);
-            float4 o = p.fb.temp[y * p.fb.w + x];
-            o.x += rc.x;
-            o.y += rc.y;
-            o.z += rc.z;
-            o.w += 0.0f;
-            p.fb.temp[y * p.fb.w + x] = o;
-        }
-    }
-    uint32_t n = cnt.nodes, l = cnt.leaves;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        n += __shfl_xor_sync(0xffffffffu, n, off);
-        l += __shfl_xor_sync(0xffffffffu, l, off);
-    }
-    if (lane == 0 && (n | l)) {
-        atomicAdd(&p.totals[TOT_NODES], (unsigned long long)n);
-        atomicAdd(&p.totals[TOT_LEAVES], (unsigned long long)l);
     }
 }
 

@@ -224,7 +224,11 @@ RT_DEV bool intersect_mtri(const MTri *__restrict__ tri, v3 ro, v3 rd, int prim_
 }
 
 struct SceneGeo {
-    const WNode *__restrict__ nodes;
+    const WNode *__restrict__ nodes;  // as uploaded (wbvh_node_t)
+    const WNode *__restrict__ dnodes; // device-built copy the trace kernels walk (rt_trace.cuh: k_build_dnodes)
+    const uint32_t *__restrict__ blas_roots; // per mesh instance: node word of its BLAS root
+    const void *__restrict__ dmtris;         // triangle blocks re-laid out for the 4-lane leaf test (k_build_dmtris)
+    uint32_t tlas_root_word;
     const MTri *__restrict__ mtris;
     const uint32_t *__restrict__ tri_indices;
     const TriMat *__restrict__ tri_materials;

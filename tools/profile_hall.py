@@ -9,7 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-from ray_b200 import capi, scenes
+from ray_b200 import capi, scenes, cuda as _cuda
+if os.environ.get("RC_DEV_CUDA_LIB"):  # A/B runs of an alternative build of the kernels (dev tool only)
+    _cuda.LIB_PATH = os.path.abspath(os.environ["RC_DEV_CUDA_LIB"])
+import hashlib
 import oracle
 from common import Pair
 
@@ -51,7 +54,9 @@ dt = time.time() - t0
 c = pair.ctx.counters()
 k = pair.ctx.kernel_ms()
 rays = c["primary_rays"] + c["secondary_rays"]
-print(json.dumps({"wall_s": dt, "ms_per_sample": dt / args.spp * 1e3, "Mrays_s": rays / dt / 1e6,
+raw = pair.ctx.readback(capi.RC_BUF_RAW)
+print(json.dumps({"lib": os.path.basename(_cuda.LIB_PATH), "fin_min": os.environ.get("RC_TRACE_FIN_MIN"),
+                  "raw_sha1": hashlib.sha1(raw.tobytes()).hexdigest()[:16], "wall_s": dt, "ms_per_sample": dt / args.spp * 1e3, "Mrays_s": rays / dt / 1e6,
                   "Mshadow_s": c["shadow_rays"] / dt / 1e6, "counters": c, "kernel_ms": k,
                   "rays_per_sample": rays / args.spp, "nodes_per_ray": c["nodes_visited"] / max(rays + c["shadow_rays"], 1),
-                  "leaves_per_ray": c["leaves_tested"] / max(rays + c["shadow_rays"], 1)}, indent=1))
+                  "leaves_per_ray": c["leaves_tested"] / max(rays + c["shadow_rays"], 1)}))
