@@ -4,6 +4,8 @@
 #include "SceneCuda.h"
 
 #include <algorithm>
+#include <array>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 
@@ -206,6 +208,23 @@ Scene::~Scene() {
     }
 }
 
+// the rc_texture table FillView hands out; rebuilt under the unique lock (AddTexture / Finalize) so concurrent
+// renderers preparing the same scene under the shared lock only read it
+void Scene::RebuildTexViews_nolock() {
+    tex_views_.clear();
+    for (const TexImage &img : textures_) {
+        rc_texture t = {};
+        t.handle = img.handle;
+        t.channels = img.channels;
+        for (int lod = 0; lod < RC_TEX_MIP_LEVELS; ++lod) { // no mips: every level aliases level 0
+            t.res[lod][0] = uint16_t(img.w);
+            t.res[lod][1] = uint16_t(img.h);
+            t.pixels[lod] = img.pixels.data();
+        }
+        tex_views_.push_back(t);
+    }
+}
+
 void Scene::RefreshPinnedMirrors_nolock() {
     if (getenv("RAY_HOST_NO_PINNED")) { // A/B switch for measurements
         pinned_revision_ = 0;
@@ -307,7 +326,8 @@ TextureHandle Scene::AddTexture(const tex_desc_t &t) {
         ret |= rt::kTexReconstructZBitHost;
     }
     textures_.push_back(std::move(img));
-    ++revision_;
+    RebuildTexViews_nolock();
+    revision_ = NextRevision();
     return TextureHandle{ret, 0};
 }
 
@@ -432,6 +452,102 @@ MaterialHandle Scene::AddMaterial(const principled_mat_desc_t &m) {
     return root;
 }
 
+uint64_t Scene::NextRevision() {
+    static std::atomic<uint64_t> counter{1};
+    return counter.fetch_add(1);
+}
+
+// Tangent frame of a mesh that came without binormals: per triangle the uv-aligned tangent / binormal, accumulated at
+// the vertices; a vertex whose triangles disagree on the orientation of either is duplicated (up to three twins), the
+// triangle re-pointed to the twin.  Finally b = normalize(cross(n, accumulated tangent)).
+// Reference: Ray::ComputeTangentBasis, internal/TextureUtils.cpp:1603-1739 (same arithmetic, restated over plain arrays).
+static void ComputeTangentBasis(std::vector<rt::Vertex> &verts, std::vector<uint32_t> &idx) {
+    const float FLT_EPS_ = 0.0000001f;
+    const size_t n0 = verts.size();
+    std::vector<std::array<uint32_t, 3>> twins(n0, std::array<uint32_t, 3>{0, 0, 0});
+    std::vector<std::array<float, 3>> bin(n0, std::array<float, 3>{0.0f, 0.0f, 0.0f});
+    auto dot = [](const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    for (size_t i = 0; i + 2 < idx.size(); i += 3) {
+        const uint32_t id[3] = {idx[i], idx[i + 1], idx[i + 2]};
+        float dp1[3], dp2[3];
+        for (int a = 0; a < 3; ++a) {
+            dp1[a] = verts[id[1]].p[a] - verts[id[0]].p[a];
+            dp2[a] = verts[id[2]].p[a] - verts[id[0]].p[a];
+        }
+        const float dt1[2] = {verts[id[1]].t[0] - verts[id[0]].t[0], verts[id[1]].t[1] - verts[id[0]].t[1]};
+        const float dt2[2] = {verts[id[2]].t[0] - verts[id[0]].t[0], verts[id[2]].t[1] - verts[id[0]].t[1]};
+        float tangent[3], binormal[3];
+        const float det = fabsf(dt1[0] * dt2[1] - dt1[1] * dt2[0]);
+        if (det > FLT_EPS_) {
+            const float inv_det = 1.0f / det;
+            for (int a = 0; a < 3; ++a) {
+                tangent[a] = (dp1[a] * dt2[1] - dp2[a] * dt1[1]) * inv_det;
+                binormal[a] = (dp2[a] * dt1[0] - dp1[a] * dt2[0]) * inv_det;
+            }
+        } else {
+            float plane_n[3];
+            cross3(dp1, dp2, plane_n);
+            int w = 2;
+            tangent[0] = 0.0f, tangent[1] = 1.0f, tangent[2] = 0.0f;
+            if (fabsf(plane_n[0]) <= fabsf(plane_n[1]) && fabsf(plane_n[0]) <= fabsf(plane_n[2])) {
+                tangent[0] = 1.0f, tangent[1] = 0.0f, tangent[2] = 0.0f;
+                w = 1;
+            } else if (fabsf(plane_n[2]) <= fabsf(plane_n[0]) && fabsf(plane_n[2]) <= fabsf(plane_n[1])) {
+                tangent[0] = 0.0f, tangent[1] = 0.0f, tangent[2] = 1.0f;
+                w = 0;
+            }
+            if (fabsf(plane_n[w]) > FLT_EPS_) {
+                cross3(plane_n, tangent, binormal);
+                float l = len3(binormal);
+                for (int a = 0; a < 3; ++a) {
+                    binormal[a] /= l;
+                }
+                cross3(plane_n, binormal, tangent);
+                l = len3(tangent);
+                for (int a = 0; a < 3; ++a) {
+                    tangent[a] /= l;
+                }
+            } else {
+                for (int a = 0; a < 3; ++a) {
+                    binormal[a] = tangent[a] = 0.0f;
+                }
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t vi = id[c];
+            const int i1 = dot(verts[vi].b, tangent) < 0.0f ? 1 : 0;
+            const int i2 = dot(bin[vi].data(), binormal) < 0.0f ? 2 : 0;
+            uint32_t target = vi;
+            if (i1 || i2) {
+                uint32_t &twin = twins[vi][i1 + i2 - 1];
+                if (twin == 0) {
+                    twin = uint32_t(verts.size());
+                    rt::Vertex copy = verts[vi];
+                    copy.b[0] = copy.b[1] = copy.b[2] = 0.0f;
+                    verts.push_back(copy);
+                }
+                target = twin;
+                idx[i + c] = target;
+            } else {
+                bin[vi] = {binormal[0], binormal[1], binormal[2]};
+            }
+            for (int a = 0; a < 3; ++a) {
+                verts[target].b[a] += tangent[a];
+            }
+        }
+    }
+    for (rt::Vertex &v : verts) {
+        if (fabsf(v.b[0]) > FLT_EPS_ || fabsf(v.b[1]) > FLT_EPS_ || fabsf(v.b[2]) > FLT_EPS_) {
+            float b[3];
+            cross3(v.n, v.b, b);
+            const float l = len3(b);
+            if (l > FLT_EPS_) {
+                v.b[0] = b[0] / l, v.b[1] = b[1] / l, v.b[2] = b[2] / l;
+            }
+        }
+    }
+}
+
 // reference SceneCPU.cpp:342-546 + Core.cpp:260-328
 MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
     const rs_vtx_attribute &P = m.vtx_positions;
@@ -450,10 +566,12 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
     const uint32_t vtx_base = uint32_t(vertices_.size());
     const uint32_t tri_base = uint32_t(tri_materials_.size());
 
-    // vertices (binormals only matter for normal maps, which this backend does not have: any orthogonal vector will do)
-    vertices_.resize(vtx_base + n_verts);
+    // vertices; without explicit binormals the tangent frame is derived from the uv mapping, which may split vertices
+    // whose triangles disagree on handedness (reference SceneCPU.cpp:503-526, ComputeTangentBasis TextureUtils.cpp:1603)
+    std::vector<rt::Vertex> nv(n_verts);
     for (uint32_t i = 0; i < n_verts; ++i) {
-        rt::Vertex &v = vertices_[vtx_base + i];
+        rt::Vertex &v = nv[i];
+        memset(&v, 0, sizeof(v));
         memcpy(v.p, &P.data[P.offset + size_t(i) * P.stride], 3 * sizeof(float));
         if (m.vtx_normals.data) {
             memcpy(v.n, &m.vtx_normals.data[m.vtx_normals.offset + size_t(i) * m.vtx_normals.stride], 3 * sizeof(float));
@@ -462,22 +580,26 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
         }
         if (m.vtx_uvs.data) {
             memcpy(v.t, &m.vtx_uvs.data[m.vtx_uvs.offset + size_t(i) * m.vtx_uvs.stride], 2 * sizeof(float));
-        } else {
-            v.t[0] = v.t[1] = 0.0f;
         }
         if (m.vtx_binormals.data) {
             memcpy(v.b, &m.vtx_binormals.data[m.vtx_binormals.offset + size_t(i) * m.vtx_binormals.stride], 3 * sizeof(float));
-        } else {
-            const float up[3] = {fabsf(v.n[1]) < 0.999f ? 0.0f : 1.0f, fabsf(v.n[1]) < 0.999f ? 1.0f : 0.0f, 0.0f};
-            float b[3];
-            cross3(v.n, up, b);
-            const float l = len3(b);
-            v.b[0] = l > 0 ? b[0] / l : 1.0f, v.b[1] = l > 0 ? b[1] / l : 0.0f, v.b[2] = l > 0 ? b[2] / l : 0.0f;
         }
     }
+    std::vector<uint32_t> ni(m.vtx_indices_count);
+    for (uint64_t i = 0; i < m.vtx_indices_count; ++i) {
+        ni[i] = m.vtx_indices[i] + uint32_t(m.base_vertex);
+        if (ni[i] >= n_verts) {
+            log_->Error("Ray(CUDA): AddMesh: vertex index %u out of range (%u vertices)", ni[i], n_verts);
+            return MeshHandle{};
+        }
+    }
+    if (!m.vtx_binormals.data) {
+        ComputeTangentBasis(nv, ni);
+    }
+    vertices_.insert(vertices_.end(), nv.begin(), nv.end());
     vtx_indices_.resize(size_t(tri_base) * 3 + m.vtx_indices_count);
     for (uint64_t i = 0; i < m.vtx_indices_count; ++i) {
-        vtx_indices_[size_t(tri_base) * 3 + i] = vtx_base + m.vtx_indices[i] + uint32_t(m.base_vertex);
+        vtx_indices_[size_t(tri_base) * 3 + i] = vtx_base + ni[i];
     }
     tri_materials_.resize(tri_base + n_tris, rt::TriMat{0xffff, 0xffff});
 
@@ -604,7 +726,7 @@ void Scene::RemoveMesh(MeshHandle m) {
         meshes_[m._index].alive = false;
         for (size_t i = 0; i < mesh_instances_.size(); ++i) {
             if (mesh_instances_[i].mesh_index == m._index) {
-                instance_alive_[i] = 0;
+                RemoveMeshInstance_nolock(uint32_t(i));
             }
         }
     }
@@ -825,17 +947,21 @@ void Scene::SetMeshInstanceTransform(MeshInstanceHandle h, const float *xform) {
     }
 }
 
-void Scene::RemoveMeshInstance(MeshInstanceHandle h) {
-    std::unique_lock<std::shared_timed_mutex> lock(mtx_);
-    if (h._index < mesh_instances_.size()) {
-        instance_alive_[h._index] = 0;
-        // its emissive-triangle lights go with it
+// reference SceneCPU.cpp RemoveMeshInstance_nolock: the instance's emissive-triangle lights go with it
+void Scene::RemoveMeshInstance_nolock(uint32_t index) {
+    if (index < mesh_instances_.size()) {
+        instance_alive_[index] = 0;
         for (size_t i = 0; i < lights_.size(); ++i) {
-            if (l_type(lights_[i]) == rt::LIGHT_TRI && f2u(lights_[i].p[1]) == h._index) {
+            if (l_type(lights_[i]) == rt::LIGHT_TRI && f2u(lights_[i].p[1]) == index) {
                 light_alive_[i] = 0;
             }
         }
     }
+}
+
+void Scene::RemoveMeshInstance(MeshInstanceHandle h) {
+    std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    RemoveMeshInstance_nolock(h._index);
 }
 
 // reference SceneCommon.cpp:121-170 + Core.cpp:1321-1366 (ConstructCamera)
@@ -942,7 +1068,8 @@ void Scene::Finalize(const ParallelFor &) {
     RebuildTLAS_nolock();
     RebuildLightTree_nolock();
     GetBounds(bounds_min_, bounds_max_);
-    ++revision_;
+    revision_ = NextRevision();
+    RebuildTexViews_nolock();
     RefreshPinnedMirrors_nolock();
 }
 
@@ -1469,18 +1596,6 @@ void Scene::FillView(rc_scene_view &v) const {
                 const_cast<rc_array *>(dst[i])->ptr = pinned_[i].ptr;
             }
         }
-    }
-    tex_views_.clear();
-    for (const TexImage &img : textures_) {
-        rc_texture t = {};
-        t.handle = img.handle;
-        t.channels = img.channels;
-        for (int lod = 0; lod < RC_TEX_MIP_LEVELS; ++lod) { // no mips: every level aliases level 0
-            t.res[lod][0] = uint16_t(img.w);
-            t.res[lod][1] = uint16_t(img.h);
-            t.pixels[lod] = img.pixels.data();
-        }
-        tex_views_.push_back(t);
     }
     v.textures = tex_views_.empty() ? nullptr : tex_views_.data();
     v.texture_count = uint32_t(tex_views_.size());

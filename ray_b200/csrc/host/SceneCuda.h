@@ -37,7 +37,7 @@ class Scene final : public SceneBase {
     };
     std::vector<TexImage> textures_;
     uint32_t tex_storage_counts_[4] = {0, 0, 0, 0};
-    mutable std::vector<rc_texture> tex_views_;
+    std::vector<rc_texture> tex_views_; // rebuilt by AddTexture / Finalize (unique lock)
     // Page-locked copies of the big geometry arrays, refreshed by Finalize: FillView hands these to rc_upload_scene so a
     // (re-)upload is a straight DMA at PCIe speed instead of the driver staging pageable vectors through a bounce buffer.
     struct PinnedMirror {
@@ -83,12 +83,16 @@ class Scene final : public SceneBase {
     environment_desc_t env_{};
     uint32_t tlas_root_ = 0xffffffffu;
     float bounds_min_[3] = {0, 0, 0}, bounds_max_[3] = {0, 0, 0};
-    mutable uint64_t revision_ = 1; // bumped by Finalize: tells the renderer to re-upload
+    // process-wide unique, so (scene address, revision) never repeats for a new scene at a recycled address
+    static uint64_t NextRevision();
+    mutable uint64_t revision_ = NextRevision(); // renewed by Finalize: tells the renderer to re-upload
 
     void RebuildTLAS_nolock();
     void RebuildLightTree_nolock();
     MaterialHandle AddMaterial_nolock(const shading_node_desc_t &m);
     uint32_t AddLight_nolock(const rt::Light &l);
+    void RemoveMeshInstance_nolock(uint32_t index);
+    void RebuildTexViews_nolock();
 
   public:
     explicit Scene(ILog *log);

@@ -435,8 +435,9 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     const int max_bounces = p.ps.max_total_depth;
     const bool do_sort = (pass->flags & RC_RENDER_NO_SORT) == 0;
 
-    if (ctx->sample_pending) {
-        // event slots are reused per sample: collect the previous sample's timings first
+    if (ctx->sample_pending && ctx->stats_enabled) {
+        // event slots are reused per sample: collect the previous sample's timings first.  Without statistics nothing
+        // is harvested and samples queue up back to back (RC_RENDER_ASYNC keeps the GPU fed across samples).
         CU_CHECK(ctx, cudaStreamSynchronize(s));
         harvest_stats(ctx);
     }
@@ -534,7 +535,7 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
         k_accumulate_totals<<<1, 32, 0, s>>>(p, max_bounces);
     }
     record(ctx, EV_BOUNCE0 + kEventsPerBounce * kMaxBounces);
-    ctx->sample_pending = true;
+    ctx->sample_pending = ctx->stats_enabled;
     ctx->pending_bounces = max_bounces;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -799,6 +800,10 @@ int rc_resize(rc_ctx *ctx, int w, int h) {
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t n = size_t(w) * h;
+    // the old buffers go one by one below: a failure half-way must leave the context unrenderable (fill_params checks
+    // for a zero-size frame), not pointing at freed or mis-sized planes
+    ctx->w = ctx->h = ctx->fb.w = ctx->fb.h = 0;
+    ctx->ray_capacity = 0;
     if (dev_alloc(ctx, &ctx->fb.temp, n) || dev_alloc(ctx, &ctx->fb.full, n) || dev_alloc(ctx, &ctx->fb.half, n) ||
         dev_alloc(ctx, &ctx->fb.raw, n) || dev_alloc(ctx, &ctx->fb.final, n) || dev_alloc(ctx, &ctx->fb.base_color, n) ||
         dev_alloc(ctx, &ctx->fb.depth_normals, n) || dev_alloc(ctx, &ctx->fb.required_samples, n)) {
