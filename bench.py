@@ -37,7 +37,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hall-diffuse", choices=["hall-diffuse", "hall-principled", "cornell"])
+    ap.add_argument("--workload", default="hall-diffuse", choices=["hall-diffuse", "hall-principled", "cornell", "c5-instanced"])
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the extra BASELINE.json configs (#1, #3, #5) at N=1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--gather-every", type=int, default=0, help="steps per framebuffer gather (0 = once per timed batch)")
@@ -53,7 +54,37 @@ def make_desc(workload, w, h):
         return scenes.hall("diffuse", w, h)
     if workload == "hall-principled":
         return scenes.hall("principled", w, h)
+    if workload == "c5-instanced":
+        return scenes.c5_instanced(w, h)
     return scenes.cornell_box(w, h)
+
+
+def host_cores():
+    """Host threads this process can really use: affinity mask capped by the cgroup cpu quota (a 1-GPU lease of a big
+    node reports 128 logical CPUs but may be throttled to a fraction of them)."""
+    info = {"cpu_count": os.cpu_count() or 1}
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else info["cpu_count"]
+    info["affinity"] = n
+    info["cgroup_quota"] = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                txt = f.read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    info["cgroup_quota"] = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        info["cgroup_quota"] = q / float(f2.read().split()[0])
+            break
+        except Exception:
+            continue
+    if info["cgroup_quota"]:
+        n = max(1, min(n, int(info["cgroup_quota"] + 0.5)))
+    info["threads"] = n
+    return info
 
 
 class ClockSampler:
@@ -192,7 +223,8 @@ def cpu_reference_run(workload, sample, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle
     from ray_b200 import capi, scenes
-    threads = os.cpu_count() or 1
+    cores = host_cores()
+    threads = int(os.environ.get("BENCH_CPU_THREADS", "0")) or cores["threads"]
     if sample == "auto":
         # ~10-30 s of CPU work: a 16th of the frame per 16 hardware threads (at least 480x270), 2 spp per step
         sample = "1920x1080x2" if threads >= 128 else ("960x540x2" if threads >= 24 else "480x270x2")
@@ -216,9 +248,73 @@ def cpu_reference_run(workload, sample, steps, warmup):
     value = rps * spp * steps / secs / 1e6
     return {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
             "sample": f"{workload} at {w}x{h}, {spp} spp per step x {steps} steps, Ray::{rname} renderer "
-                      f"(unmodified reference, oracle/_ref), {threads} threads over {tile}x{tile} tiles; rays/sample counted "
-                      f"once with the reference's Ref:: stage functions ({rps})",
-            "seconds": secs, "ms_per_step": secs / steps * 1e3}
+                      f"(unmodified reference, oracle/_ref), {threads} threads over {tile}x{tile} tiles "
+                      f"(os.cpu_count {cores['cpu_count']}, affinity {cores['affinity']}, cgroup quota {cores['cgroup_quota']}); "
+                      f"rays/sample counted once with the reference's Ref:: stage functions ({rps})",
+            "seconds": secs, "ms_per_step": secs / steps * 1e3, "spp_per_step": spp, "frame": f"{w}x{h}",
+            "host": cores}
+
+
+def cpu_single_thread_ref(workload, w, h, spp):
+    """config #1 is quoted on RendererRef, single thread: time it on a bounded number of samples."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from ray_b200 import capi, scenes
+    desc = make_desc(workload, w, h)
+    osc = scenes.build(desc, oracle.Scene(wide=False))
+    rps = rays_per_sample_ref(osc, w, h)
+    r = oracle.Renderer(capi.RT_REFERENCE, w, h)
+    r.render_mt(osc, 1, 1, 64)
+    secs = r.render_mt(osc, spp, 1, 64)
+    return {"value": rps * spp / secs / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"{workload} {w}x{h}, {spp} spp, Ray::Reference renderer (RendererRef, BVH2), 1 thread"}
+
+
+def measure_config(workload, w, h, steps, warmup, device=0):
+    """One more BASELINE.json config on one GPU: device-timed K steps (scene resident) + the blocking public-API path."""
+    import ctypes as C
+    from ray_b200 import cuda, host, scenes
+    t0 = time.perf_counter()
+    desc = make_desc(workload, w, h)
+    r = host.Renderer(w, h, device=device)
+    s = scenes.build(desc, r.create_scene())
+    build_s = time.perf_counter() - t0
+    lib = cuda.load_library()
+    ctx = r.native_context()
+    rect = (0, 0, w, h)
+    it = 0
+    for _ in range(warmup):
+        it = r.render(s, rect, it, 1)
+    r.reset_stats()
+    lib.rc_event_record(ctx, 0)
+    it = r.render(s, rect, it, steps)
+    lib.rc_event_record(ctx, 1)
+    f = C.c_float(0)
+    lib.rc_event_elapsed_ms(ctx, 0, 1, C.byref(f))
+    ms = float(f.value)
+    c = r.counters()
+    rays = c["primary_rays"] + c["secondary_rays"]
+    kms = r.kernel_ms()
+    # e2e: one blocking RenderScene + frame read-back per step (scene already resident: it did not change)
+    r.pixels(host.RAW, copy=False)
+    r.reset_stats()
+    e2e_steps = max(min(steps, 4), 1)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        it = r.render(s, rect, it, 1)
+        r.pixels(host.RAW, copy=False)
+    e2e_s = time.perf_counter() - t0
+    c2 = r.counters()
+    out = {"workload": f"{workload} {w}x{h}", "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "steps": steps,
+           "ms_per_step": ms / steps, "rays_per_step": rays / steps, "shadow_rays_per_step": c["shadow_rays"] / steps,
+           "e2e": {"value": (c2["primary_rays"] + c2["secondary_rays"]) / e2e_s / 1e6, "unit": UNIT,
+                   "d2h_bytes_per_step": w * h * 16, "h2d_bytes_per_step": 256, "steps": e2e_steps},
+           "triangles": desc.triangle_count(), "instances": len(desc.instances), "bvh8_nodes": s.node_count(),
+           "scene_build_s": build_s, "family_ms": {k: round(v[0], 3) for k, v in kms.items()},
+           "nodes_per_ray": c["nodes_visited"] / max(rays + c["shadow_rays"], 1)}
+    s.close()
+    r.close()
+    return out
 
 
 def main():
@@ -236,6 +332,7 @@ def main():
         if rank != 0:
             return 0
         base = cpu_reference_run(a.workload, a.cpu_sample, a.steps, a.warmup)
+        config = dict(config, spp_per_step=base["spp_per_step"], frame=base["frame"], parallelism=f"{base['cores']} host threads")
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -388,12 +485,28 @@ def main():
                      "Mshadow_per_s": shadow_total / (ms * 1e-3) / 1e6},
             "scene": {"triangles": desc.triangle_count(), "bvh8_nodes": s.node_count(), "scene_bytes": int(scene_bytes)},
             "roofline": roofline(c, kms, a.steps)}
+    if a.gpus == 1 and not a.no_extra_configs and a.workload == "hall-diffuse":
+        # the other single-GPU configurations of BASELINE.json, measured in the same run (bounded steps each)
+        extra = {}
+        for key, wl, ww, hh, st, wu in (("config1_cornell_256x256_64spp", "cornell", 256, 256, 64, 3),
+                                        ("config3_hall_principled_1080p", "hall-principled", 1920, 1080, 8, 3),
+                                        ("config5_instanced_10M_4096x4096", "c5-instanced", 4096, 4096, 4, 3)):
+            try:
+                extra[key] = measure_config(wl, ww, hh, st, wu, local_rank)
+            except Exception as e:
+                extra[key] = {"error": str(e)}
+        if not a.no_cpu_baseline:
+            try:
+                extra["config1_cornell_256x256_64spp"]["cpu_baseline"] = cpu_single_thread_ref("cornell", 256, 256, 8)
+            except Exception as e:
+                extra["config1_cornell_256x256_64spp"]["cpu_baseline"] = {"error": str(e)}
+        line["configs"] = extra
     if not a.no_cpu_baseline and a.gpus == 1:
         try:
             base = cpu_reference_run(a.workload, a.cpu_sample, 2, 1)
-            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "host")}
         except Exception as e:  # the oracle is test infrastructure: its absence must not hide the GPU number
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores()["threads"], "kind": "reference",
                                     "sample": f"unavailable: {e}"}
     print(json.dumps(line))
     if use_dist:

@@ -862,4 +862,83 @@ void ro_view_trace_shadow_rays(const rc_scene_view *v, const rc_camera *cam, int
                          rand_seed_for(iteration), iteration, vs.textures, w, reinterpret_cast<color_rgba_t *>(temp));
 }
 
+// One sample of the whole RenderScene sequence (the loop body of Cpu::Renderer<P>::RenderScene, RendererCPU.h:374-606)
+// through the reference's own Ref:: stage functions over CALLER-PROVIDED scene arrays, `threads` threads over row
+// strips (every pixel is independent: SURVEY.md section 8(e)).  `temp` (w*h RGBA, zeroed by the caller) receives the
+// radiance of this sample; rays[0] / rays[1] += closest-hit / shadow rays traced.  Camera (primary rays) comes from
+// `cam_scene` (any scene holding the same camera).  Lets a GPU test compare the CUDA backend BITWISE with the reference
+// code on the arrays built by the product's own host layer, at full frame size, in seconds.
+void ro_view_render_sample(const rc_scene_view *v, const rc_camera *cam, ro_scene *cam_scene, int w, int h, int iteration,
+                           int threads, float *temp, unsigned long long rays_out[2]) {
+    OracleScene *cs = reinterpret_cast<OracleScene *>(cam_scene);
+    const camera_t &camera = cs->cam();
+    const std::vector<float> table = make_filter_table(camera.filter, camera.filter_width);
+    const pass_settings_t ps = pass_from(*cam);
+    const uint32_t seed = rand_seed_for(iteration);
+    threads = std::max(threads, 1);
+    const int rows = (h + threads - 1) / threads;
+    std::atomic<unsigned long long> n_rays{0}, n_shadow{0};
+    auto worker = [&](int y0) {
+        const int y1 = std::min(h, y0 + rows);
+        if (y0 >= y1) {
+            return;
+        }
+        ViewScene vs;
+        const scene_data_t sd = vs.make(*v);
+        aligned_vector<Ref::ray_data_t> rays, sec;
+        aligned_vector<Ref::hit_data_t> hits;
+        aligned_vector<Ref::shadow_ray_t> sh;
+        Ref::GeneratePrimaryRays(camera, rect_t{0, y0, w, y1 - y0}, w, h, __pmj02_samples, seed, table.data(), iteration,
+                                 nullptr, rays, hits);
+        color_rgba_t *out = reinterpret_cast<color_rgba_t *>(temp);
+        std::vector<uint32_t> def_sky;
+        int count = int(rays.size());
+        for (int bounce = 0; bounce <= int(ps.max_total_depth) && count != 0; ++bounce) {
+            if (v->tlas_root != 0xffffffff) {
+                Ref::TraceRays(Span<Ref::ray_data_t>{rays.data(), count}, int(ps.min_transp_depth), int(ps.max_transp_depth),
+                               sd, v->tlas_root, bounce != 0, vs.textures, __pmj02_samples, seed, iteration,
+                               Span<Ref::hit_data_t>{hits.data(), count});
+            }
+            n_rays += uint64_t(count);
+            sec.resize(size_t(count) + 1);
+            sh.resize(size_t(count) + 1);
+            def_sky.resize(size_t(count) + 1);
+            int n_sec = 0, n_sh = 0, n_sky = 0;
+            const Span<const Ref::hit_data_t> hs{hits.data(), count};
+            const Span<const Ref::ray_data_t> rs{rays.data(), count};
+            if (bounce == 0) {
+                Ref::ShadePrimary(ps, hs, rs, __pmj02_samples, seed, iteration, eSpatialCacheMode::None, sd, vs.textures,
+                                  sec.data(), &n_sec, sh.data(), &n_sh, def_sky.data(), &n_sky, w, 1.0f / float(iteration),
+                                  out, nullptr, nullptr); // AOV planes are not compared here
+            } else {
+                const float clamp_direct = (bounce == 1) ? ps.clamp_direct : ps.clamp_indirect;
+                Ref::ShadeSecondary(ps, clamp_direct, hs, rs, __pmj02_samples, seed, iteration, eSpatialCacheMode::None, sd,
+                                    vs.textures, sec.data(), &n_sec, sh.data(), &n_sh, def_sky.data(), &n_sky, w, out,
+                                    nullptr, nullptr);
+            }
+            if (v->tlas_root != 0xffffffff && n_sh != 0) {
+                Ref::TraceShadowRays(Span<const Ref::shadow_ray_t>{sh.data(), n_sh}, int(ps.max_transp_depth),
+                                     bounce == 0 ? ps.clamp_direct : ps.clamp_indirect, sd, v->tlas_root, __pmj02_samples,
+                                     seed, iteration, vs.textures, w, out);
+            }
+            n_shadow += uint64_t(n_sh);
+            rays.assign(sec.begin(), sec.begin() + n_sec);
+            hits.assign(size_t(n_sec), Ref::hit_data_t{});
+            count = n_sec;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        pool.emplace_back(worker, t * rows);
+    }
+    worker(0);
+    for (auto &t : pool) {
+        t.join();
+    }
+    if (rays_out) {
+        rays_out[0] += n_rays.load();
+        rays_out[1] += n_shadow.load();
+    }
+}
+
 } // extern "C"

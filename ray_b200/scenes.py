@@ -348,11 +348,13 @@ def instanced(n_instances=64, tris_per_blas=2000, width=512, height=512, seed=99
 
     sa, si = _grid_mesh(res, res, sph, flip=True)
     s.meshes.append(MeshDesc(sa, si, [(m_a, m_a, 0, len(si))]))
-    ga, gi = _flat_quad((-12, 0, -12), (-12, 0, 12), (12, 0, 12), (12, 0, -12), (0, 1, 0))
-    la, li = _flat_quad((-3, 7, -3), (3, 7, -3), (3, 7, 3), (-3, 7, 3), (0, -1, 0))
+    side = int(np.ceil(np.sqrt(n_instances)))
+    g = max(12.0, 0.8 * side + 2.0)  # ground half-size: covers the instance grid (12 m for the small test scenes)
+    ls = 3.0 * g / 12.0
+    ga, gi = _flat_quad((-g, 0, -g), (-g, 0, g), (g, 0, g), (g, 0, -g), (0, 1, 0))
+    la, li = _flat_quad((-ls, 7, -ls), (ls, 7, -ls), (ls, 7, ls), (-ls, 7, ls), (0, -1, 0))
     s.meshes.append(MeshDesc(np.concatenate([ga, la]), np.concatenate([gi, li + np.uint32(4)]),
                              [(m_g, m_g, 0, 6), (m_l, capi.RS_INVALID, 6, 6)]))
-    side = int(np.ceil(np.sqrt(n_instances)))
     for i in range(n_instances):
         gx, gz = i % side, i // side
         ang = rng.uniform(0, 2 * np.pi)
@@ -366,8 +368,16 @@ def instanced(n_instances=64, tris_per_blas=2000, width=512, height=512, seed=99
     s.instances.append((1, IDENTITY.T.reshape(16), {}))
     fwd = np.array([0.0, -0.45, -1.0])
     fwd /= np.linalg.norm(fwd)
-    s.camera = capi.rs_camera_desc.default(origin=(0.0, 6.0, 12.0), fwd=tuple(fwd.astype(np.float32)), fov=50.0,
+    s.camera = capi.rs_camera_desc.default(origin=(0.0, 6.0 * g / 12.0, g), fwd=tuple(fwd.astype(np.float32)), fov=50.0,
                                            filter=capi.FILTER_BOX, max_diff_depth=8, max_total_depth=8)
+    return s
+
+
+def c5_instanced(width=4096, height=4096) -> SceneDesc:
+    """BASELINE.json config #5: 10 M instanced triangles = a TLAS over 1,000 instances (rotation + non-uniform scale,
+    seed 99) of one 10,000-triangle BLAS, diffuse, 4096 x 4096 -- the traversal-divergence stress."""
+    s = instanced(1000, 10000, width, height, seed=99)
+    s.name = "c5-instanced"
     return s
 
 

@@ -71,6 +71,8 @@ def load():
                                  vp, vp, C.c_int, vp, P(C.c_int), vp, P(C.c_int), vp, vp, vp]),
         "ro_view_trace_shadow_rays": (None, [P(capi.rc_scene_view), P(capi.rc_camera), C.c_int, C.c_int, vp, C.c_int,
                                              C.c_float, vp]),
+        "ro_view_render_sample": (None, [P(capi.rc_scene_view), P(capi.rc_camera), vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         vp, P(C.c_ulonglong)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -253,6 +255,34 @@ class ViewScene:
         shadow_rays = np.ascontiguousarray(shadow_rays)
         self.lib.ro_view_trace_shadow_rays(C.byref(self.view), C.byref(self.cam), w, iteration, _ptr(shadow_rays),
                                            len(shadow_rays), float(clamp_val), _ptr(temp))
+
+
+def host_threads():
+    """Threads this process may actually use: the affinity mask, capped by the cgroup cpu quota when there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def view_render(view, cam, cam_scene, w, h, spp, threads=None, first_iteration=1):
+    """`spp` samples of the whole RenderScene sequence through the reference's Ref:: stage functions over caller-provided
+    scene arrays (multi-threaded over row strips), accumulated like RendererCPU.h:607-633 (exposure 0: full += (temp -
+    full) / iteration, in float32).  Returns (full image (h, w, 4) float32, closest-hit rays traced, shadow rays traced)."""
+    lib = load()
+    threads = threads or host_threads()
+    full = np.zeros((h, w, 4), np.float32)
+    counts = (C.c_ulonglong * 2)(0, 0)
+    for it in range(first_iteration, first_iteration + spp):
+        temp = np.zeros((h, w, 4), np.float32)
+        lib.ro_view_render_sample(C.byref(view), C.byref(cam), cam_scene.h, w, h, it, threads, _ptr(temp), counts)
+        full += (temp - full) * (np.float32(1.0) / np.float32(it))
+    return full, int(counts[0]), int(counts[1])
 
 
 def render_with_stages(sc, gen_scene, w, h, spp, max_bounces=8):

@@ -254,3 +254,20 @@ def test_builtin_sampler_table_is_a_02_sequence_per_dimension():
                 cells = ix * (1 << (m - a)) + iy
                 assert len(np.unique(cells)) == n, (d, m, a)
     assert len({t[d].tobytes() for d in range(32)}) == 32
+
+
+def test_view_render_reproduces_renderer_ref(oracle_mod):
+    """oracle.view_render (the multi-threaded Ref:: stage sequence the at-size GPU parity tests compare against) over the
+    reference's OWN arrays is RendererRef, bit for bit."""
+    desc = scenes.cornell_box(48, 40)
+    osc = scenes.build(desc, oracle_mod.Scene(wide=True))
+    ref = oracle_mod.Renderer(capi.RT_REFERENCE, 48, 40)
+    it = 0
+    for _ in range(3):
+        it = ref.render(osc, (0, 0, 48, 40), it)
+    raw = ref.pixels(1)
+    full, n_rays, n_shadow = oracle_mod.view_render(osc.view(), osc.camera(), osc, 48, 40, 3, threads=3)
+    assert np.array_equal(full, raw)
+    assert n_rays > 3 * 48 * 40 and n_shadow > 0
+    ref.close()
+    osc.close()
