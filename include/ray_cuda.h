@@ -182,6 +182,37 @@ void *rc_device_ptr(rc_ctx *ctx, int which);
 int rc_event_record(rc_ctx *ctx, int slot);
 int rc_event_elapsed_ms(rc_ctx *ctx, int slot_a, int slot_b, float *ms);
 
+/* asynchronous variant of rc_readback: enqueues the 2-D copy on the context's stream and returns; `dst` should be
+ * page-locked (rc_host_alloc) for the copy to overlap; complete after rc_sync */
+int rc_readback_async(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch);
+
+/* ---- multi-GPU: one process, one rc_ctx per device, the frame sharded in row strips ----
+ * A communicator groups n contexts that were sized (rc_resize) to the SAME full frame and hold the same scene and
+ * tables.  The rows of the frame are owned by a fixed device: band r = rc_comm_strip({0,0,W,H}, n, r) (heights differ
+ * by <= 1 row), because a pixel's running means must keep accumulating where their history lives.  rc_comm_render
+ * intersects pass->rect with every band, enqueues one sample of each non-empty piece on its device and, unless
+ * RC_RENDER_ASYNC is set, waits for all of them.  There is no inter-bounce communication: a pixel depends only on
+ * (x, y, iteration, scene).
+ * rc_gather   : every device copies ITS rows of plane `which` inside `rect` (NULL = the rect of the last
+ *               rc_comm_render) straight into the caller's host image (dst = top-left pixel of `rect`, pitch in
+ *               pixels), n PCIe links in parallel; `dst` should be page-locked (rc_host_alloc).  Blocking.
+ * rc_gather_device : peer copies (NVLink) of the other devices' rows into ctxs[0]'s plane, so device 0 holds the whole
+ *               rect (for a consumer on the device: denoiser, display).  Blocking. */
+typedef struct rc_comm rc_comm;
+int rc_comm_init(rc_ctx **ctxs, int n, rc_comm **out_comm);
+void rc_comm_destroy(rc_comm *comm);
+const char *rc_comm_last_error(const rc_comm *comm);
+/* strip of `rect` owned by context `rank` of an n-context communicator */
+int rc_comm_strip(const rc_rect *rect, int n, int rank, rc_rect *out);
+int rc_comm_upload_scene(rc_comm *comm, const rc_scene_view *scene);
+int rc_comm_upload_tables(rc_comm *comm, const uint32_t *pmj, int dims, int samples, const float *filter_table,
+                          int filter_table_size);
+int rc_comm_render(rc_comm *comm, const rc_pass_desc *pass);
+int rc_comm_sync(rc_comm *comm);
+int rc_gather(rc_comm *comm, int which, const rc_rect *rect, float *dst, int pitch);
+int rc_gather_device(rc_comm *comm, int which, const rc_rect *rect);
+int rc_comm_get_counters(rc_comm *comm, rc_counters *out); /* summed over the devices */
+
 /* ---- stage entry points (host AoS buffers in the reference's layouts; see header comment) ---- */
 /* rays_out: ray_data_t[rect.w*rect.h] (72 B), hits_out: hit_data_t[...] (20 B); *count_out = rays generated. */
 int rc_stage_generate_primary_rays(rc_ctx *ctx, const rc_pass_desc *pass, void *rays_out, void *hits_out,

@@ -23,6 +23,10 @@ typedef struct rh_scene rh_scene;
 
 /* Ray::CreateRenderer(settings_t{w,h,preferred_device}, log, parallel_for, CUDA).  NULL when no sm_100 device exists. */
 rh_renderer *rh_create_renderer(int w, int h, int device);
+/* several devices of this node: `devices` is settings_t::preferred_device of the CUDA backend ("0,1,2,3", "0-7", "all");
+ * the frame is sharded over them in row bands (rc_comm_* of ray_cuda.h) */
+rh_renderer *rh_create_renderer_multi(int w, int h, const char *devices);
+int rh_device_count(rh_renderer *r);
 void rh_destroy_renderer(rh_renderer *r);
 const char *rh_device_name(rh_renderer *r);
 int rh_error_count(rh_renderer *r);

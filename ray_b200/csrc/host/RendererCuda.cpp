@@ -76,17 +76,69 @@ RendererBase *CreateRenderer(const settings_t &s, ILog *log, const ParallelFor &
 
 namespace Cuda {
 
-Renderer::Renderer(const settings_t &s, ILog *log) : log_(log) {
-    int device = 0;
-    if (!s.preferred_device.empty()) {
-        device = atoi(std::string(s.preferred_device).c_str());
+// settings_t::preferred_device: "" = device 0, "3" = device 3, "0,1,2,3" / "0-7" / "all" = several devices of this node
+// (the frame is sharded over them in row bands)
+static std::vector<int> parse_devices(std::string_view spec) {
+    std::vector<int> out;
+    const std::string s(spec);
+    if (s.empty()) {
+        return {0};
     }
-    const int rc = rc_create(device, &ctx_);
-    if (rc != 0 || !ctx_) {
-        ctx_ = nullptr;
-        throw std::runtime_error("no usable sm_100 CUDA device (rc_create code " + std::to_string(rc) + ")");
+    if (s == "all") {
+        for (int i = 0; i < rc_device_count(); ++i) {
+            out.push_back(i);
+        }
+        return out;
+    }
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(',', pos);
+        if (end == std::string::npos) {
+            end = s.size();
+        }
+        const std::string tok = s.substr(pos, end - pos);
+        const size_t dash = tok.find('-');
+        if (dash != std::string::npos && dash > 0) {
+            for (int i = atoi(tok.substr(0, dash).c_str()); i <= atoi(tok.substr(dash + 1).c_str()); ++i) {
+                out.push_back(i);
+            }
+        } else if (!tok.empty()) {
+            out.push_back(atoi(tok.c_str()));
+        }
+        pos = end + 1;
+    }
+    return out;
+}
+
+Renderer::Renderer(const settings_t &s, ILog *log) : log_(log) {
+    const std::vector<int> devices = parse_devices(s.preferred_device);
+    if (devices.empty()) {
+        throw std::runtime_error("no CUDA device selected by preferred_device");
+    }
+    for (const int device : devices) {
+        rc_ctx *c = nullptr;
+        const int rc = rc_create(device, &c);
+        if (rc != 0 || !c) {
+            for (rc_ctx *o : ctxs_) {
+                rc_destroy(o);
+            }
+            ctxs_.clear();
+            throw std::runtime_error("no usable sm_100 CUDA device " + std::to_string(device) + " (rc_create code " +
+                                     std::to_string(rc) + ")");
+        }
+        ctxs_.push_back(c);
+    }
+    ctx_ = ctxs_[0];
+    if (ctxs_.size() > 1 && rc_comm_init(ctxs_.data(), int(ctxs_.size()), &comm_) != 0) {
+        for (rc_ctx *o : ctxs_) {
+            rc_destroy(o);
+        }
+        throw std::runtime_error("rc_comm_init failed (one context per device is required)");
     }
     device_name_ = rc_device_name(ctx_);
+    if (ctxs_.size() > 1) {
+        device_name_ += " x" + std::to_string(ctxs_.size());
+    }
     log_->Info("============================================================================");
     log_->Info("Device       is %s", device_name_.c_str());
     if (s.use_spatial_cache) {
@@ -99,8 +151,9 @@ Renderer::Renderer(const settings_t &s, ILog *log) : log_(log) {
 
 Renderer::~Renderer() {
     FreeMirrors();
-    if (ctx_) {
-        rc_destroy(ctx_);
+    rc_comm_destroy(comm_);
+    for (rc_ctx *c : ctxs_) {
+        rc_destroy(c);
     }
 }
 
@@ -116,10 +169,13 @@ void Renderer::Resize(const int w, const int h) {
     if (w == w_ && h == h_) {
         return;
     }
-    if (rc_resize(ctx_, w, h) != 0) {
-        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
-        return;
+    for (rc_ctx *c : ctxs_) { // every device holds full-size planes; only its band of rows is ever rendered there
+        if (rc_resize(c, w, h) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(c));
+            return;
+        }
     }
+    frame_on_dev0_ = false;
     w_ = w;
     h_ = h;
     const size_t n = size_t(w) * h;
@@ -140,8 +196,10 @@ void Renderer::Resize(const int w, const int h) {
 }
 
 void Renderer::Clear(const color_rgba_t &c) {
-    if (rc_clear(ctx_, c.v) != 0) {
-        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+    for (rc_ctx *x : ctxs_) {
+        if (rc_clear(x, c.v) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(x));
+        }
     }
 }
 
@@ -160,19 +218,23 @@ bool Renderer::Prepare(const Scene &s, const camera_t &cam) {
         tables_dirty_ = true;
     }
     if (tables_dirty_) {
-        if (rc_upload_tables(ctx_, sampler_table_.data(), rt::kRandDims, rt::kRandSamples, filter_table_.data(),
-                             int(filter_table_.size())) != 0) {
-            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
-            return false;
+        for (rc_ctx *c : ctxs_) {
+            if (rc_upload_tables(c, sampler_table_.data(), rt::kRandDims, rt::kRandSamples, filter_table_.data(),
+                                 int(filter_table_.size())) != 0) {
+                log_->Error("Ray(CUDA): %s", rc_last_error(c));
+                return false;
+            }
         }
         tables_dirty_ = false;
     }
     if (uploaded_scene_ != &s || uploaded_revision_ != s.revision()) {
         rc_scene_view v;
         s.FillView(v);
-        if (rc_upload_scene(ctx_, &v) != 0) {
-            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
-            return false;
+        for (rc_ctx *c : ctxs_) { // replicated: every band needs the whole scene
+            if (rc_upload_scene(c, &v) != 0) {
+                log_->Error("Ray(CUDA): %s", rc_last_error(c));
+                return false;
+            }
         }
         uploaded_scene_ = &s;
         uploaded_revision_ = s.revision();
@@ -206,14 +268,24 @@ void Renderer::RenderSceneBatch(const SceneBase &scene, RegionContext &region, c
     for (int i = 0; i < count; ++i) {
         ++region.iteration;
         p.iteration = region.iteration;
-        if (rc_render(ctx_, &p) != 0) {
+        if (comm_) {
+            if (rc_comm_render(comm_, &p) != 0) {
+                log_->Error("Ray(CUDA): %s", rc_comm_last_error(comm_));
+                break;
+            }
+        } else if (rc_render(ctx_, &p) != 0) {
             log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
             break;
         }
     }
-    if (rc_sync(ctx_) != 0) {
+    if (comm_) {
+        if (rc_comm_sync(comm_) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_comm_last_error(comm_));
+        }
+    } else if (rc_sync(ctx_) != 0) {
         log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
     }
+    frame_on_dev0_ = false;
     final_dirty_ = raw_dirty_ = base_dirty_ = dn_dirty_ = true;
 }
 
@@ -222,6 +294,13 @@ void Renderer::Readback(const int which, color_rgba_t *dst) const {
         return;
     }
     const rc_rect r{0, 0, w_, h_};
+    if (comm_ && !frame_on_dev0_) {
+        // every device copies its own band straight into the page-locked mirror: N PCIe links in parallel
+        if (rc_gather(comm_, which, &r, &dst[0].v[0], w_) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_comm_last_error(comm_));
+        }
+        return;
+    }
     if (rc_readback(ctx_, which, &r, &dst[0].v[0], w_) != 0) {
         log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
     }
@@ -263,6 +342,19 @@ color_data_rgba_t Renderer::get_aux_pixels_ref(const eAUXBuffer buf) const {
 void Renderer::DenoiseImage(const RegionContext &region) {
     const rect_t &r = region.rect();
     const rc_rect rr = {r.x, r.y, r.w, r.h};
+    if (comm_) {
+        // the filter reads a neighbourhood across band borders: bring the planes it needs onto device 0 (NVLink peer
+        // copies) and filter there; pixels are then read back from device 0 until the next RenderScene
+        const rc_rect frame{0, 0, w_, h_};
+        for (const int plane : {RC_BUF_FULL, RC_BUF_HALF, RC_BUF_RAW, RC_BUF_BASE_COLOR, RC_BUF_DEPTH_NORMALS, RC_BUF_TEMP}) {
+            if (rc_gather_device(comm_, plane, &frame) != 0) {
+                log_->Error("Ray(CUDA): %s", rc_comm_last_error(comm_));
+                return;
+            }
+        }
+        frame_on_dev0_ = true;
+        base_dirty_ = dn_dirty_ = true;
+    }
     if (rc_denoise_nlm(ctx_, &rr, region.iteration) != 0) {
         log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
         return;

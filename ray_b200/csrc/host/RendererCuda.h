@@ -19,7 +19,10 @@ namespace Cuda {
 
 class Renderer final : public RendererBase {
     ILog *log_;
-    rc_ctx *ctx_ = nullptr;
+    rc_ctx *ctx_ = nullptr;          // device 0 of this renderer (the only one unless several were asked for)
+    std::vector<rc_ctx *> ctxs_;      // all devices; the frame is sharded over them in row bands (include/ray_cuda.h)
+    rc_comm *comm_ = nullptr;         // non-null when ctxs_.size() > 1
+    mutable bool frame_on_dev0_ = false; // a denoise pass gathered the frame onto device 0: read back from there
     int w_ = 0, h_ = 0;
     std::string device_name_;
 
@@ -77,6 +80,8 @@ class Renderer final : public RendererBase {
     /// end-to-end measurements).
     void InvalidateScene() { uploaded_scene_ = nullptr; }
     rc_ctx *native_context() const { return ctx_; }
+    rc_comm *native_comm() const { return comm_; }
+    int device_count() const { return int(ctxs_.size()); }
 };
 
 std::vector<uint32_t> GenerateSamplerTable();                                   // SamplerTable.cpp

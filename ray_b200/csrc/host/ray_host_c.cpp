@@ -43,13 +43,19 @@ inline Cuda::Scene *S(rh_scene *s) { return reinterpret_cast<Cuda::Scene *>(s); 
 
 extern "C" {
 
-rh_renderer *rh_create_renderer(int w, int h, int device) {
+static rh_renderer *create_renderer(int w, int h, const std::string &dev);
+
+rh_renderer *rh_create_renderer(int w, int h, int device) { return create_renderer(w, h, std::to_string(device)); }
+
+// devices: settings_t::preferred_device of the CUDA backend ("3", "0,1,2,3", "0-7", "all")
+rh_renderer *rh_create_renderer_multi(int w, int h, const char *devices) { return create_renderer(w, h, devices ? devices : ""); }
+
+static rh_renderer *create_renderer(int w, int h, const std::string &dev) {
     auto box = std::make_unique<RendererBox>();
     box->log = std::make_unique<CollectLog>();
     settings_t st;
     st.w = w;
     st.h = h;
-    const std::string dev = std::to_string(device);
     st.preferred_device = dev;
     RendererBase *r = CreateRenderer(st, box->log.get(), parallel_for_serial, 1u << uint32_t(eRendererType::CUDA));
     if (!r) {
@@ -147,7 +153,14 @@ void rh_get_stats(rh_renderer *r, uint64_t us[11]) {
     }
 }
 void rh_reset_stats(rh_renderer *r) { R(r)->ResetStats(); }
-void rh_get_counters(rh_renderer *r, rc_counters *out) { rc_get_counters(R(r)->native_context(), out); }
+void rh_get_counters(rh_renderer *r, rc_counters *out) {
+    if (R(r)->native_comm()) {
+        rc_comm_get_counters(R(r)->native_comm(), out);
+    } else {
+        rc_get_counters(R(r)->native_context(), out);
+    }
+}
+int rh_device_count(rh_renderer *r) { return R(r)->device_count(); }
 void rh_get_kernel_ms(rh_renderer *r, double ms[6], uint64_t launches[6]) { rc_get_kernel_ms(R(r)->native_context(), ms, launches); }
 void rh_set_sampler_table(rh_renderer *r, const uint32_t *table) { R(r)->SetSamplerTable(table); }
 void rh_set_render_flags(rh_renderer *r, uint32_t f) { R(r)->SetRenderFlags(f); }

@@ -363,6 +363,19 @@ int build_traversal_copies(rc_ctx *ctx, const rc_scene_view *sv) {
     return 0;
 }
 
+const float4 *plane_of(const rc_ctx *ctx, int which) {
+    switch (which) {
+    case RC_BUF_FINAL: return ctx->fb.final;
+    case RC_BUF_RAW: return ctx->fb.raw;
+    case RC_BUF_BASE_COLOR: return ctx->fb.base_color;
+    case RC_BUF_DEPTH_NORMALS: return ctx->fb.depth_normals;
+    case RC_BUF_FULL: return ctx->fb.full;
+    case RC_BUF_HALF: return ctx->fb.half;
+    case RC_BUF_TEMP: return ctx->fb.temp;
+    default: return nullptr;
+    }
+}
+
 float clamp_limit(float v) { return (v != 0.0f) ? 3.0f * v : 3.402823466e+38F; }
 
 int persistent_grid(const rc_ctx *ctx, int blocks_per_sm) { return ctx->num_sms * blocks_per_sm; }
@@ -1191,6 +1204,266 @@ int rc_readback(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pit
     CU_CHECK(ctx, cudaMemcpy2D(dst, size_t(pitch) * sizeof(float4), src + size_t(rect->y) * ctx->w + rect->x,
                                size_t(ctx->w) * sizeof(float4), size_t(rect->w) * sizeof(float4), rect->h,
                                cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rc_readback_async(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch) {
+    if (!ctx || !rect || !dst) {
+        return fail(ctx, "rc_readback_async: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    const float4 *src = plane_of(ctx, which);
+    if (!src) {
+        return fail(ctx, "rc_readback_async: unknown buffer %d", which);
+    }
+    if (rect->x < 0 || rect->y < 0 || rect->w <= 0 || rect->h <= 0 || rect->x + rect->w > ctx->w ||
+        rect->y + rect->h > ctx->h || pitch < rect->w) {
+        return fail(ctx, "rc_readback_async: bad rect/pitch");
+    }
+    CU_CHECK(ctx, cudaMemcpy2DAsync(dst, size_t(pitch) * sizeof(float4), src + size_t(rect->y) * ctx->w + rect->x,
+                                    size_t(ctx->w) * sizeof(float4), size_t(rect->w) * sizeof(float4), rect->h,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// ---- multi-GPU: one process, one context per device, row strips ---------------------------
+struct rc_comm {
+    std::vector<rc_ctx *> ctxs;
+    std::vector<char> peer_ok; // ctxs[0] can address ctxs[r]'s memory
+    rc_rect last_rect{0, 0, 0, 0};
+    std::string last_error;
+};
+
+namespace {
+int comm_fail(rc_comm *c, const char *fmt, ...) {
+    char buf[1024];
+    va_list vl;
+    va_start(vl, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, vl);
+    va_end(vl);
+    if (c) {
+        c->last_error = buf;
+    }
+    return 1;
+}
+} // namespace
+
+int rc_comm_strip(const rc_rect *rect, int n, int rank, rc_rect *out);
+
+namespace {
+// Rows of the FRAME are owned by a fixed device (band r of the full height), whatever region a call renders: the
+// running means of a pixel (full / half / AOV planes) must keep accumulating on the device that holds their history.
+// Returns false when `rect` does not touch band r.
+bool comm_band(const rc_comm *comm, int r, const rc_rect &rect, rc_rect *out) {
+    const rc_ctx *c0 = comm->ctxs[0];
+    const rc_rect frame{0, 0, c0->w, c0->h};
+    rc_rect band;
+    rc_comm_strip(&frame, int(comm->ctxs.size()), r, &band);
+    const int y0 = rect.y > band.y ? rect.y : band.y;
+    const int y1 = (rect.y + rect.h) < (band.y + band.h) ? (rect.y + rect.h) : (band.y + band.h);
+    if (y1 <= y0 || rect.w <= 0) {
+        return false;
+    }
+    *out = rc_rect{rect.x, y0, rect.w, y1 - y0};
+    return true;
+}
+} // namespace
+
+int rc_comm_strip(const rc_rect *rect, int n, int rank, rc_rect *out) {
+    if (!rect || !out || n <= 0 || rank < 0 || rank >= n) {
+        return 1;
+    }
+    const int base = rect->h / n, rem = rect->h % n;
+    out->x = rect->x;
+    out->w = rect->w;
+    out->y = rect->y + rank * base + (rank < rem ? rank : rem);
+    out->h = base + (rank < rem ? 1 : 0);
+    return 0;
+}
+
+int rc_comm_init(rc_ctx **ctxs, int n, rc_comm **out_comm) {
+    if (!ctxs || n <= 0 || !out_comm) {
+        return 1;
+    }
+    auto *c = new rc_comm();
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i]) {
+            delete c;
+            return 1;
+        }
+        for (int j = 0; j < i; ++j) {
+            if (ctxs[j]->device == ctxs[i]->device) {
+                delete c;
+                return 1; // one context per device
+            }
+        }
+        c->ctxs.push_back(ctxs[i]);
+    }
+    c->peer_ok.assign(n, 0);
+    c->peer_ok[0] = 1;
+    cudaSetDevice(ctxs[0]->device);
+    for (int i = 1; i < n; ++i) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctxs[0]->device, ctxs[i]->device);
+        if (can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[i]->device, 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) {
+                c->peer_ok[i] = 1;
+            }
+            cudaGetLastError();
+        }
+    }
+    *out_comm = c;
+    return 0;
+}
+
+void rc_comm_destroy(rc_comm *comm) { delete comm; }
+
+const char *rc_comm_last_error(const rc_comm *comm) { return comm ? comm->last_error.c_str() : "null communicator"; }
+
+int rc_comm_upload_scene(rc_comm *comm, const rc_scene_view *scene) {
+    if (!comm) {
+        return 1;
+    }
+    for (rc_ctx *ctx : comm->ctxs) { // replicated: the whole scene is needed by every strip
+        if (rc_upload_scene(ctx, scene) != 0) {
+            return comm_fail(comm, "device %d: %s", ctx->device, rc_last_error(ctx));
+        }
+    }
+    return 0;
+}
+
+int rc_comm_upload_tables(rc_comm *comm, const uint32_t *pmj, int dims, int samples, const float *filter_table,
+                          int filter_table_size) {
+    if (!comm) {
+        return 1;
+    }
+    for (rc_ctx *ctx : comm->ctxs) {
+        if (rc_upload_tables(ctx, pmj, dims, samples, filter_table, filter_table_size) != 0) {
+            return comm_fail(comm, "device %d: %s", ctx->device, rc_last_error(ctx));
+        }
+    }
+    return 0;
+}
+
+int rc_comm_sync(rc_comm *comm) {
+    if (!comm) {
+        return 1;
+    }
+    int rc = 0;
+    for (rc_ctx *ctx : comm->ctxs) {
+        if (rc_sync(ctx) != 0) {
+            rc = comm_fail(comm, "device %d: %s", ctx->device, rc_last_error(ctx));
+        }
+    }
+    return rc;
+}
+
+int rc_comm_render(rc_comm *comm, const rc_pass_desc *pass) {
+    if (!comm || !pass) {
+        return 1;
+    }
+    const int n = int(comm->ctxs.size());
+    for (int r = 0; r < n; ++r) {
+        rc_ctx *ctx = comm->ctxs[r];
+        if (ctx->w != comm->ctxs[0]->w || ctx->h != comm->ctxs[0]->h) {
+            return comm_fail(comm, "rc_comm_render: context %d is sized %dx%d, context 0 %dx%d", r, ctx->w, ctx->h,
+                             comm->ctxs[0]->w, comm->ctxs[0]->h);
+        }
+        rc_pass_desc p = *pass;
+        if (!comm_band(comm, r, pass->rect, &p.rect)) {
+            continue;
+        }
+        p.flags |= RC_RENDER_ASYNC; // every device gets its strip queued before anyone is waited for
+        if (rc_render(ctx, &p) != 0) {
+            return comm_fail(comm, "device %d: %s", ctx->device, rc_last_error(ctx));
+        }
+    }
+    comm->last_rect = pass->rect;
+    if ((pass->flags & RC_RENDER_ASYNC) == 0) {
+        return rc_comm_sync(comm);
+    }
+    return 0;
+}
+
+int rc_gather(rc_comm *comm, int which, const rc_rect *rect, float *dst, int pitch) {
+    if (!comm || !dst) {
+        return 1;
+    }
+    const rc_rect full = rect ? *rect : comm->last_rect;
+    const int n = int(comm->ctxs.size());
+    if (pitch < full.w || full.w <= 0 || full.h <= 0) {
+        return comm_fail(comm, "rc_gather: bad rect/pitch");
+    }
+    for (int r = 0; r < n; ++r) { // n independent device->host copies, each on its own device's link
+        rc_rect s;
+        if (!comm_band(comm, r, full, &s)) {
+            continue;
+        }
+        float *d = dst + (size_t(s.y - full.y) * size_t(pitch)) * 4; // dst addresses the top-left pixel of `rect`
+        if (rc_readback_async(comm->ctxs[r], which, &s, d, pitch) != 0) {
+            return comm_fail(comm, "device %d: %s", comm->ctxs[r]->device, rc_last_error(comm->ctxs[r]));
+        }
+    }
+    return rc_comm_sync(comm);
+}
+
+int rc_gather_device(rc_comm *comm, int which, const rc_rect *rect) {
+    if (!comm) {
+        return 1;
+    }
+    const rc_rect full = rect ? *rect : comm->last_rect;
+    const int n = int(comm->ctxs.size());
+    rc_ctx *c0 = comm->ctxs[0];
+    float4 *dst = const_cast<float4 *>(plane_of(c0, which));
+    if (!dst) {
+        return comm_fail(comm, "rc_gather_device: unknown buffer %d", which);
+    }
+    if (rc_comm_sync(comm) != 0) {
+        return 1;
+    }
+    for (int r = 1; r < n; ++r) {
+        rc_ctx *cr = comm->ctxs[r];
+        rc_rect s;
+        if (!comm_band(comm, r, full, &s)) {
+            continue;
+        }
+        const float4 *src = plane_of(cr, which);
+        cudaSetDevice(cr->device);
+        cudaMemcpy3DPeerParms pp = {};
+        pp.srcDevice = cr->device;
+        pp.dstDevice = c0->device;
+        pp.srcPtr = make_cudaPitchedPtr(const_cast<float4 *>(src), size_t(cr->w) * sizeof(float4), cr->w, cr->h);
+        pp.dstPtr = make_cudaPitchedPtr(dst, size_t(c0->w) * sizeof(float4), c0->w, c0->h);
+        pp.srcPos = make_cudaPos(size_t(s.x) * sizeof(float4), s.y, 0);
+        pp.dstPos = make_cudaPos(size_t(s.x) * sizeof(float4), s.y, 0);
+        pp.extent = make_cudaExtent(size_t(s.w) * sizeof(float4), s.h, 1);
+        const cudaError_t e = cudaMemcpy3DPeerAsync(&pp, cr->stream); // NVLink when peer access is on, staged otherwise
+        if (e != cudaSuccess) {
+            return comm_fail(comm, "rc_gather_device: peer copy %d -> %d failed: %s", cr->device, c0->device,
+                             cudaGetErrorString(e));
+        }
+    }
+    return rc_comm_sync(comm);
+}
+
+int rc_comm_get_counters(rc_comm *comm, rc_counters *out) {
+    if (!comm || !out) {
+        return 1;
+    }
+    memset(out, 0, sizeof(*out));
+    for (rc_ctx *ctx : comm->ctxs) {
+        rc_counters c;
+        if (rc_get_counters(ctx, &c) != 0) {
+            return comm_fail(comm, "device %d: %s", ctx->device, rc_last_error(ctx));
+        }
+        out->primary_rays += c.primary_rays;
+        out->secondary_rays += c.secondary_rays;
+        out->shadow_rays += c.shadow_rays;
+        out->nodes_visited += c.nodes_visited;
+        out->leaves_tested += c.leaves_tested;
+        out->samples = c.samples > out->samples ? c.samples : out->samples;
+    }
     return 0;
 }
 

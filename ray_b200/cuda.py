@@ -66,6 +66,18 @@ def load_library():
         "rc_device_ptr": (vp, [vp, C.c_int]),
         "rc_event_record": (C.c_int, [vp, C.c_int]),
         "rc_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, P(C.c_float)]),
+        "rc_readback_async": (C.c_int, [vp, C.c_int, P(capi.rc_rect), vp, C.c_int]),
+        "rc_comm_init": (C.c_int, [P(vp), C.c_int, P(vp)]),
+        "rc_comm_destroy": (None, [vp]),
+        "rc_comm_last_error": (C.c_char_p, [vp]),
+        "rc_comm_strip": (C.c_int, [P(capi.rc_rect), C.c_int, C.c_int, P(capi.rc_rect)]),
+        "rc_comm_upload_scene": (C.c_int, [vp, P(capi.rc_scene_view)]),
+        "rc_comm_upload_tables": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int]),
+        "rc_comm_render": (C.c_int, [vp, P(capi.rc_pass_desc)]),
+        "rc_comm_sync": (C.c_int, [vp]),
+        "rc_gather": (C.c_int, [vp, C.c_int, P(capi.rc_rect), vp, C.c_int]),
+        "rc_gather_device": (C.c_int, [vp, C.c_int, P(capi.rc_rect)]),
+        "rc_comm_get_counters": (C.c_int, [vp, P(capi.rc_counters)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not export what include/ray_cuda.h declares
@@ -81,7 +93,9 @@ EXPORTED_SYMBOLS = [
     "rc_enable_stats", "rc_get_stats", "rc_get_counters", "rc_reset_stats", "rc_get_kernel_ms",
     "rc_stage_generate_primary_rays", "rc_stage_trace_rays", "rc_stage_shade", "rc_stage_trace_shadow_rays",
     "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
-    "rc_event_record", "rc_event_elapsed_ms",
+    "rc_event_record", "rc_event_elapsed_ms", "rc_readback_async", "rc_comm_init", "rc_comm_destroy", "rc_comm_last_error",
+    "rc_comm_strip", "rc_comm_upload_scene", "rc_comm_upload_tables", "rc_comm_render", "rc_comm_sync", "rc_gather",
+    "rc_gather_device", "rc_comm_get_counters",
 ]
 
 

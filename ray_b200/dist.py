@@ -72,3 +72,82 @@ def device_frame_tensor(renderer, which, device_index: int):
     if not ptr:
         raise RuntimeError("rc_device_ptr returned NULL")
     return torch.as_tensor(DeviceImage(ptr, renderer.hh, renderer.w), device=torch.device("cuda", device_index))
+
+
+class SharedHostFrame:
+    """ONE host frame shared by all ranks of a node: every rank copies its own strip device->host straight into it, so N
+    PCIe links work in parallel and rank 0 never has to pull N strips through its own link (the end-to-end delivery path;
+    the NCCL gather above stays for consumers that want the frame on a device).
+
+    The block is POSIX shared memory created by rank 0 and attached by the others (name passed through the process
+    group); on a CUDA machine each rank page-locks its mapping (cudaHostRegister) so the strip copy is a full-speed DMA.
+    `rows(y, h)` is the (h, w, 4) float32 numpy view of rows [y, y + h); `ptr(y)` the address of row y."""
+
+    def __init__(self, w: int, h: int, pin: bool = True):
+        import numpy as np
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.w, self.h = w, h
+        self.nbytes = w * h * 16
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        self.rank = rank
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            name = [self.shm.name]
+        else:
+            name = [None]
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.array = np.ndarray((h, w, 4), dtype=np.float32, buffer=self.shm.buf)
+        self.pinned = False
+        if pin:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+                    self.pinned = (int(rc) == 0)
+            except Exception:
+                self.pinned = False
+
+    def ptr(self, y: int = 0) -> int:
+        return self.array.ctypes.data + y * self.w * 16
+
+    def rows(self, y: int, h: int):
+        return self.array[y:y + h]
+
+    def close(self):
+        import torch.distributed as dist
+        if self.pinned:
+            try:
+                import torch
+                torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            except Exception:
+                pass
+        self.array = None
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.barrier()
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+def deliver_strip(renderer, which, rect, frame: SharedHostFrame):
+    """Copy this rank's strip `rect` of plane `which` device->host into the shared frame (blocking)."""
+    import ctypes as C
+
+    from . import capi, cuda
+
+    lib = cuda.load_library()
+    ctx = renderer.native_context()
+    x, y, w, h = rect
+    r = capi.rc_rect(x, y, w, h)
+    if lib.rc_readback_async(ctx, which, C.byref(r), C.c_void_p(frame.ptr(y) + x * 16), frame.w) != 0:
+        raise RuntimeError(lib.rc_last_error(ctx).decode())
+    if lib.rc_sync(ctx) != 0:
+        raise RuntimeError(lib.rc_last_error(ctx).decode())

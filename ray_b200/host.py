@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libray_host.so")
 FINAL, RAW, BASE_COLOR, DEPTH_NORMALS = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
-    "rh_create_renderer", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
+    "rh_create_renderer", "rh_create_renderer_multi", "rh_device_count", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
     "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_denoise", "rh_add_texture", "rh_add_material_node",
     "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_add_light_directional",
     "rh_add_light_sphere", "rh_add_light_spot", "rh_add_light_rect", "rh_add_light_disk", "rh_add_light_line",
@@ -45,6 +45,8 @@ def load_library():
     u32 = C.c_uint32
     sig = {
         "rh_create_renderer": (vp, [C.c_int, C.c_int, C.c_int]),
+        "rh_create_renderer_multi": (vp, [C.c_int, C.c_int, C.c_char_p]),
+        "rh_device_count": (C.c_int, [vp]),
         "rh_destroy_renderer": (None, [vp]),
         "rh_device_name": (C.c_char_p, [vp]),
         "rh_error_count": (C.c_int, [vp]),
@@ -210,9 +212,13 @@ class Scene:
 class Renderer:
     """Cuda::Renderer (RendererBase) through the C wrapper."""
 
-    def __init__(self, w, h, device=0):
+    def __init__(self, w, h, device=0, devices=None):
+        """`devices` (e.g. "0,1,2,3", "0-7", "all") shards the frame over several GPUs of this node in one process."""
         self.lib = load_library()
-        self.h = self.lib.rh_create_renderer(w, h, device)
+        if devices is not None:
+            self.h = self.lib.rh_create_renderer_multi(w, h, str(devices).encode())
+        else:
+            self.h = self.lib.rh_create_renderer(w, h, device)
         if not self.h:
             raise HostError("Ray::CreateRenderer(CUDA) failed: no usable sm_100 CUDA device (there is no CPU fallback)")
         self.w, self.hh = w, h

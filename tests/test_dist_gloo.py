@@ -54,3 +54,56 @@ def test_gather_strips_world2_gloo(tmp_path, h):
     want = np.broadcast_to(rows * 1000 + cols, (h, w, 4)) + np.array([0.0, 0.25, 0.5, 0.75], np.float32)
     assert frame.shape == (h, w, 4)
     assert np.array_equal(frame, want.astype(np.float32))
+
+
+def _shared_worker(rank, world, port, w, h, out_dir):
+    import torch.distributed as tdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    frame = rdist.SharedHostFrame(w, h, pin=False)
+    x, y, ww, hh = rdist.strip_rect(rank, world, w, h)
+    rows = np.arange(y, y + hh, dtype=np.float32).reshape(hh, 1, 1)
+    cols = np.arange(w, dtype=np.float32).reshape(1, w, 1)
+    frame.rows(y, hh)[...] = rows * 1000 + cols + np.array([0.0, 0.25, 0.5, 0.75], np.float32)  # the rank's "D2H copy"
+    tdist.barrier()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "shared.npy"), np.array(frame.array))
+    frame.close()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.parametrize("h", [12, 13])
+def test_shared_host_frame_world2_gloo(tmp_path, h):
+    """End-to-end delivery path of N > 1: each rank writes its own strip into one shared host frame."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    w, world = 9, 2
+    mp.spawn(_shared_worker, args=(world, port, w, h, str(tmp_path)), nprocs=world, join=True)
+    frame = np.load(tmp_path / "shared.npy")
+    rows = np.arange(h, dtype=np.float32).reshape(h, 1, 1)
+    cols = np.arange(w, dtype=np.float32).reshape(1, w, 1)
+    want = np.broadcast_to(rows * 1000 + cols, (h, w, 4)) + np.array([0.0, 0.25, 0.5, 0.75], np.float32)
+    assert np.array_equal(frame, want.astype(np.float32))
+
+
+def test_comm_bands_partition_any_rect():
+    """rc_comm_strip (pure arithmetic of the C-ABI): bands of the frame tile it exactly; heights differ by <= 1 row."""
+    import ctypes as C
+    from ray_b200 import capi, cuda
+    lib = cuda.load_library()
+    for n in (1, 2, 3, 8):
+        for h in (1080, 1081, 9):
+            full = capi.rc_rect(0, 0, 1920, h)
+            y = 0
+            hs = []
+            for r in range(n):
+                out = capi.rc_rect()
+                assert lib.rc_comm_strip(C.byref(full), n, r, C.byref(out)) == 0
+                assert (out.x, out.w, out.y) == (0, 1920, y)
+                y += out.h
+                hs.append(out.h)
+            assert y == h and max(hs) - min(hs) <= 1
