@@ -66,7 +66,6 @@ struct rc_ctx {
     DevArray tex_descs, tex_texels, qtree;
     DevArray dnodes, blas_roots, dmtris; // device-built traversal copies (rt_trace.cuh)
     uint32_t tlas_root_word = kEmptyChild;
-    uint32_t *d_build_flag = nullptr;
     int trace_fin_min = 32;         // lanes of a warp that must have finished before their epilogue + refill is issued
     float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
     size_t nlm_scratch_elems = 0;
@@ -297,6 +296,70 @@ int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     return 0;
 }
 
+// Walk the hierarchy the way a ray would (TLAS nodes -> instance -> its BLAS) over the caller's arrays and check what
+// the trace kernels rely on: child / instance / triangle-block indices inside their arrays, leaves that fit the
+// 27-bit + 4-bit leaf word of rt_trace.cuh.  Only nodes REACHABLE from the TLAS root are looked at: freed SparseStorage
+// slots inside the arrays' capacity hold stale bytes.  Shared BLASes are walked once.
+int validate_bvh(rc_ctx *ctx, const rc_scene_view *sv) {
+    if (sv->tlas_root == 0xffffffffu) {
+        return 0;
+    }
+    const uint32_t n_nodes = sv->wnodes.count, n_inst = sv->mesh_instances.count, n_blocks = sv->mtris.count;
+    const WNode *nodes = static_cast<const WNode *>(sv->wnodes.ptr);
+    const MeshInstance *inst = static_cast<const MeshInstance *>(sv->mesh_instances.ptr);
+    if (sv->tlas_root >= n_nodes) {
+        return fail(ctx, "rc_upload_scene: tlas_root %u outside the node array (%u)", sv->tlas_root, n_nodes);
+    }
+    std::vector<uint8_t> seen(n_nodes, 0); // bit 0: visited as a TLAS node, bit 1: as a BLAS node
+    std::vector<std::pair<uint32_t, bool>> stack;
+    stack.emplace_back(sv->tlas_root, false);
+    while (!stack.empty()) {
+        const uint32_t n = stack.back().first;
+        const bool blas = stack.back().second;
+        stack.pop_back();
+        const uint8_t bit = blas ? 2 : 1;
+        if (seen[n] & bit) {
+            continue;
+        }
+        seen[n] |= bit;
+        const WNode &nd = nodes[n];
+        if (nd.child[0] & kLeafBit) {
+            const uint32_t first = nd.child[0] & kPrimIndexBits, cnt = nd.child[1];
+            if (first >= kLeafFirstBits) {
+                return fail(ctx, "rc_upload_scene: leaf %u starts at primitive %u >= 2^27 - 1 (backend limit)", n, first);
+            }
+            if (!blas) {
+                if (first >= n_inst) {
+                    return fail(ctx, "rc_upload_scene: TLAS leaf %u names mesh instance %u of %u", n, first, n_inst);
+                }
+                const uint32_t root = inst[first].node_index;
+                if (root >= n_nodes) {
+                    return fail(ctx, "rc_upload_scene: mesh instance %u has BLAS root %u outside the node array", first, root);
+                }
+                stack.emplace_back(root, true);
+            } else {
+                const uint32_t blocks = ((first & 7u) + cnt + 7u) / 8u;
+                if (blocks == 0 || blocks > 16 || first / 8u + blocks > n_blocks) {
+                    return fail(ctx, "rc_upload_scene: BLAS leaf %u (first %u, count %u) outside the %u triangle blocks or "
+                                     "longer than 128 triangles", n, first, cnt, n_blocks);
+                }
+            }
+            continue;
+        }
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t ch = nd.child[c];
+            if (ch == kEmptyChild) {
+                continue;
+            }
+            if (ch >= n_nodes) {
+                return fail(ctx, "rc_upload_scene: node %u child %d = %u outside the node array (%u)", n, c, ch, n_nodes);
+            }
+            stack.emplace_back(ch, blas);
+        }
+    }
+    return 0;
+}
+
 // device-side copies the trace kernels walk (rt_trace.cuh): nodes with resolved child words + unhittable empty slots,
 // BLAS root word per instance, TLAS root word
 int build_traversal_copies(rc_ctx *ctx, const rc_scene_view *sv) {
@@ -322,26 +385,20 @@ int build_traversal_copies(rc_ctx *ctx, const rc_scene_view *sv) {
                                                                           static_cast<float4 *>(ctx->dmtris.ptr), n_blocks);
     }
     ctx->tlas_root_word = kEmptyChild;
-    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_build_flag, 0, sizeof(uint32_t), ctx->stream));
+    if (validate_bvh(ctx, sv)) {
+        return 1;
+    }
     if (n_nodes != 0) {
         k_build_dnodes<<<(n_nodes * 8 + 255) / 256, 256, 0, ctx->stream>>>(
-            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<WNode *>(ctx->dnodes.ptr), n_nodes, ctx->d_build_flag);
+            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<WNode *>(ctx->dnodes.ptr), n_nodes);
     }
     if (n_inst != 0) {
         k_build_blas_roots<<<(n_inst + 255) / 256, 256, 0, ctx->stream>>>(
             static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<const MeshInstance *>(ctx->mesh_instances.ptr), n_inst,
-            n_nodes, static_cast<uint32_t *>(ctx->blas_roots.ptr), ctx->d_build_flag);
+            n_nodes, static_cast<uint32_t *>(ctx->blas_roots.ptr));
     }
-    uint32_t flag = 0;
-    CU_CHECK(ctx, cudaMemcpyAsync(&flag, ctx->d_build_flag, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaGetLastError());
-    if (flag == 1) {
-        return fail(ctx, "rc_upload_scene: a BVH leaf cannot be encoded (first primitive >= 2^27 - 1 or more than 128 triangles)");
-    }
-    if (flag == 2) {
-        return fail(ctx, "rc_upload_scene: a BVH child box has min > max");
-    }
     if (sv->tlas_root != 0xffffffffu) {
         if (sv->tlas_root >= n_nodes) {
             return fail(ctx, "rc_upload_scene: tlas_root %u outside the node array (%u)", sv->tlas_root, n_nodes);
@@ -740,10 +797,6 @@ int rc_create(int device, rc_ctx **out_ctx) {
     if (const char *e = getenv("RC_TRACE_FIN_MIN")) { // development knob
         ctx->trace_fin_min = atoi(e);
     }
-    if (cudaMalloc(&ctx->d_build_flag, sizeof(uint32_t)) != cudaSuccess) {
-        rc_destroy(ctx);
-        return 6;
-    }
     cudaFuncSetAttribute(k_shade<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_shade<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_shade<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -788,7 +841,6 @@ void rc_destroy(rc_ctx *ctx) {
     cudaFree(ctx->d_filter_table);
     cudaFree(ctx->d_srgb_lut);
     cudaFree(ctx->nlm_scratch);
-    cudaFree(ctx->d_build_flag);
     for (DevArray *a : {&ctx->dnodes, &ctx->blas_roots, &ctx->dmtris, &ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
                         &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {

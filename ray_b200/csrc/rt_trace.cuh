@@ -72,19 +72,20 @@ RT_DEV f2 mul2(f2 a, f2 b) {
 //   child word of a leaf child   : kLeafBit | (blocks - 1) << 27 | first   (first = first triangle slot of a BLAS leaf,
 //                                  mesh-instance index of a TLAS leaf; blocks = 8-triangle blocks the leaf spans)
 //   empty slot                   : kEmptyChild, box = a point at +inf (never hit)
-// *bad is set to 1 if a leaf cannot be encoded (first >= 2^27 - 1 or more than 16 blocks) and to 2 if a real child has
-// an inverted box (min > max), for which "near plane by sign" would not equal the reference's min/max.
-RT_DEV uint32_t leaf_word(uint32_t c0, uint32_t c1, uint32_t *bad) {
+// Node slots inside the array's capacity that no live node points at (SparseStorage keeps stale bytes in freed slots) only
+// have to be harmless here; whether every node REACHABLE from the TLAS root can be encoded is checked on the host
+// (validate_bvh in ray_cuda.cu).  A child box is stored with its planes ordered (min <= max): the reference's slab test
+// takes min / max of the two products, so it is symmetric in the two planes, and "near plane by sign" is that same value.
+RT_DEV uint32_t leaf_word(uint32_t c0, uint32_t c1) {
     const uint32_t first = c0 & kPrimIndexBits;
     const uint32_t blocks = ((first & 7u) + c1 + 7u) / 8u;
     if (first >= kLeafFirstBits || blocks == 0 || blocks > 16) {
-        *bad = 1;
         return kEmptyChild;
     }
     return kLeafBit | ((blocks - 1u) << kLeafBlocksShift) | first;
 }
 
-__global__ void k_build_dnodes(const WNode *__restrict__ src, WNode *__restrict__ dst, uint32_t count, uint32_t *bad) {
+__global__ void k_build_dnodes(const WNode *__restrict__ src, WNode *__restrict__ dst, uint32_t count) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = gid >> 3, c = gid & 7u;
     if (n >= count) {
@@ -101,7 +102,12 @@ __global__ void k_build_dnodes(const WNode *__restrict__ src, WNode *__restrict_
         return;
     }
     const uint32_t ch = s.child[c];
-    if (ch == kEmptyChild) {
+    uint32_t word = kEmptyChild;
+    if (ch != kEmptyChild && ch < count) {
+        const uint32_t c0 = src[ch].child[0];
+        word = (c0 & kLeafBit) ? leaf_word(c0, src[ch].child[1]) : ch;
+    }
+    if (word == kEmptyChild) {
         const float inf = __int_as_float(0x7f800000);
         for (int a = 0; a < 3; ++a) {
             d.bbox_min[a][c] = inf;
@@ -112,30 +118,26 @@ __global__ void k_build_dnodes(const WNode *__restrict__ src, WNode *__restrict_
     }
     for (int a = 0; a < 3; ++a) {
         const float lo = s.bbox_min[a][c], hi = s.bbox_max[a][c];
-        if (!(lo <= hi)) {
-            *bad = 2;
-        }
-        d.bbox_min[a][c] = lo;
-        d.bbox_max[a][c] = hi;
+        d.bbox_min[a][c] = fminf(lo, hi);
+        d.bbox_max[a][c] = fmaxf(lo, hi);
     }
-    const uint32_t c0 = src[ch].child[0];
-    d.child[c] = (c0 & kLeafBit) ? leaf_word(c0, src[ch].child[1], bad) : ch;
+    d.child[c] = word;
 }
 
 // BLAS root word of every mesh instance (the root itself may be a leaf)
 __global__ void k_build_blas_roots(const WNode *__restrict__ src, const MeshInstance *__restrict__ inst, uint32_t count,
-                                   uint32_t node_count, uint32_t *__restrict__ roots, uint32_t *bad) {
+                                   uint32_t node_count, uint32_t *__restrict__ roots) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) {
         return;
     }
     const uint32_t r = inst[i].node_index;
     if (r >= node_count) {
-        roots[i] = kEmptyChild; // dead SparseStorage slot: never referenced by a TLAS leaf
+        roots[i] = kEmptyChild; // freed SparseStorage slot: never referenced by a TLAS leaf
         return;
     }
     const uint32_t c0 = src[r].child[0];
-    roots[i] = (c0 & kLeafBit) ? leaf_word(c0, src[r].child[1], bad) : r;
+    roots[i] = (c0 & kLeafBit) ? leaf_word(c0, src[r].child[1]) : r;
 }
 
 // ---- shared-memory working set of a trace block ---------------------------------------------------------------------

@@ -101,6 +101,11 @@ class SharedHostFrame:
             dist.broadcast_object_list(name, src=0)
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name[0])
+            try:  # rank 0 owns the block: keep this process's resource tracker from unlinking / warning about it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.array = np.ndarray((h, w, 4), dtype=np.float32, buffer=self.shm.buf)
         self.pinned = False
         if pin:
