@@ -36,8 +36,10 @@ class Scene final : public Cpu::Scene {
     mutable std::vector<light_t> live_lights_;
 
   public:
-    explicit Scene(ILog *log)
-        : Cpu::Scene(log, true /* wide BVH */, false /* texture compression */, false /* spatial cache */) {}
+    // texture compression as the settings ask, like the CPU backends (RendererCPU.h: CreateScene): BCn blocks and YCoCg
+    // base-colour maps are decoded through TexStorage::Fetch / YCoCg_to_RGB on the device
+    Scene(ILog *log, bool use_tex_compression)
+        : Cpu::Scene(log, true /* wide BVH */, use_tex_compression, false /* spatial cache */) {}
 
     TextureHandle AddTexture(const tex_desc_t &t) override {
         const TextureHandle h = Cpu::Scene::AddTexture(t);
@@ -197,6 +199,7 @@ class Renderer final : public RendererBase {
     ILog *log_;
     rc_ctx *ctx_ = nullptr;
     int w_ = 0, h_ = 0;
+    bool use_tex_compression_ = true;
     std::string device_name_;
     mutable std::vector<color_rgba_t> final_, raw_, base_, dn_;
     mutable bool final_dirty_ = true, raw_dirty_ = true, base_dirty_ = true, dn_dirty_ = true;
@@ -223,6 +226,7 @@ class Renderer final : public RendererBase {
             throw std::runtime_error("no usable sm_100 CUDA device");
         }
         device_name_ = rc_device_name(ctx_);
+        use_tex_compression_ = s.use_tex_compression;
         Resize(s.w, s.h);
     }
     ~Renderer() override { rc_destroy(ctx_); }
@@ -278,7 +282,7 @@ class Renderer final : public RendererBase {
             log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
         }
     }
-    SceneBase *CreateScene() override { return new Scene(log_); }
+    SceneBase *CreateScene() override { return new Scene(log_, use_tex_compression_); }
 
     void RenderScene(const SceneBase &scene, RegionContext &region) override {
         const auto *sp = dynamic_cast<const Scene *>(&scene); // pattern of RendererCPU.h:377

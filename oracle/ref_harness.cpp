@@ -79,7 +79,8 @@ CountingLog g_log;
 // Cpu::Scene keeps its arrays protected; a subclass is the documented way in (SURVEY.md section 8(c) mode 1b).
 class OracleScene final : public Cpu::Scene {
   public:
-    explicit OracleScene(bool wide) : Cpu::Scene(&g_log, wide, false /* tex compression */, false /* spatial cache */) {}
+    explicit OracleScene(bool wide, bool tex_compression = false)
+        : Cpu::Scene(&g_log, wide, tex_compression, false /* spatial cache */) {}
 
     bool wide() const { return use_wide_bvh_; }
 
@@ -283,6 +284,10 @@ int ro_cpu_features(void) {
 }
 
 ro_scene *ro_scene_create(int use_wide_bvh) { return reinterpret_cast<ro_scene *>(new OracleScene(use_wide_bvh != 0)); }
+// use_tex_compression: settings_t::use_tex_compression of the reference (BCn blocks, YCoCg-coded base colour maps)
+ro_scene *ro_scene_create_ex(int use_wide_bvh, int use_tex_compression) {
+    return reinterpret_cast<ro_scene *>(new OracleScene(use_wide_bvh != 0, use_tex_compression != 0));
+}
 void ro_scene_destroy(ro_scene *s) { delete reinterpret_cast<OracleScene *>(s); }
 
 uint32_t ro_add_texture(ro_scene *s, const rs_tex_desc *d) {
@@ -297,7 +302,7 @@ uint32_t ro_add_texture(ro_scene *s, const rs_tex_desc *d) {
     t.is_normalmap = d->is_normalmap != 0;
     t.generate_mipmaps = d->generate_mipmaps != 0;
     t.reconstruct_z = d->reconstruct_z != 0;
-    t.force_no_compression = true;
+    t.force_no_compression = false; // the scene's own use_tex_compression decides (off unless ro_scene_create_ex asked)
     const TextureHandle h = reinterpret_cast<OracleScene *>(s)->AddTexture(t);
     if (h._index != 0xffffffffu) {
         reinterpret_cast<OracleScene *>(s)->add_texture_handle(h._index);

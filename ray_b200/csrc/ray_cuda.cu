@@ -1041,16 +1041,12 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
         if (h == 0xffffffffu) {
             return 0;
         }
-        if (h & kTexYCoCgBit) {
-            return fail(ctx, "rc_upload_scene: %s %u slot %d is a YCoCg-coded texture (texture compression); not supported",
-                        what, owner, slot);
-        }
         const auto it = dense.find(h & 0xf0ffffffu);
         if (it == dense.end()) {
             return fail(ctx, "rc_upload_scene: %s %u slot %d references texture 0x%08x which is not in rc_scene_view::textures",
                         what, owner, slot, h);
         }
-        h = (h & 0x0f000000u) | it->second;
+        h = (h & 0x0f000000u) | it->second; // colour-space flags (sRGB, reconstruct-z, YCoCg) | dense id
         return 0;
     };
     for (uint32_t i = 0; i < mats.size(); ++i) {

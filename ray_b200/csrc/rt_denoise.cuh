@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(kNlmBx *kNlmBy) k_nlm_filter(NlmParams p) {
     p.fb.raw[pix] = col;
     float4 c = make_float4(tonemap_standard(col.x), tonemap_standard(col.y), tonemap_standard(col.z), col.w);
     if (p.inv_gamma != 1.0f) {
-        c.x = powf(c.x, p.inv_gamma);
-        c.y = powf(c.y, p.inv_gamma);
-        c.z = powf(c.z, p.inv_gamma);
-        c.w = powf(c.w, 1.0f);
+        c.x = libm_powf(c.x, p.inv_gamma);
+        c.y = libm_powf(c.y, p.inv_gamma);
+        c.z = libm_powf(c.z, p.inv_gamma);
+        c.w = libm_powf(c.w, 1.0f);
     }
     c.x = sse_max(0.0f, sse_min(c.x, 1.0f));
     c.y = sse_max(0.0f, sse_min(c.y, 1.0f));

@@ -441,7 +441,7 @@ RT_DEV float tonemap_standard(float c) {
     if (c < 0.0031308f) {
         return 12.92f * c;
     }
-    return 1.055f * powf(c, (1.0f / 2.4f)) - 0.055f;
+    return 1.055f * libm_powf(c, (1.0f / 2.4f)) - 0.055f;
 }
 
 __global__ void __launch_bounds__(256) k_resolve(KParams p, float exposure_mul, float mix_factor, float half_mix_factor,
@@ -473,10 +473,10 @@ __global__ void __launch_bounds__(256) k_resolve(KParams p, float exposure_mul, 
     p.fb.raw[pix] = full;
     float4 c = make_float4(tonemap_standard(full.x), tonemap_standard(full.y), tonemap_standard(full.z), full.w);
     if (inv_gamma != 1.0f) {
-        c.x = powf(c.x, inv_gamma);
-        c.y = powf(c.y, inv_gamma);
-        c.z = powf(c.z, inv_gamma);
-        c.w = powf(c.w, 1.0f);
+        c.x = libm_powf(c.x, inv_gamma);
+        c.y = libm_powf(c.y, inv_gamma);
+        c.z = libm_powf(c.z, inv_gamma);
+        c.w = libm_powf(c.w, 1.0f);
     }
     // saturate = _mm_max_ps(0, _mm_min_ps(c, 1))
     c.x = sse_max(0.0f, sse_min(c.x, 1.0f));

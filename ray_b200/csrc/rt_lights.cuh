@@ -643,7 +643,7 @@ RT_FN void sample_light_source(const bool tex_on, v3 P, v3 T, v3 B, v3 N, const 
             ls.pdf = pdf;
             const uint32_t tex_index = __float_as_uint(l.p[2]); // light_t::tri.tex_index
             if (tex_on && tex_index != kTexInvalid) {
-                const c4 tex_color = tex_sample_color(tx, tex_index, luvs, 0, rand_tex_uv);
+                const c4 tex_color = tex_sample_color(tx, tex_index, luvs, 0, rand_tex_uv, true);
                 ls.col.x *= tex_color.x;
                 ls.col.y *= tex_color.y;
                 ls.col.z *= tex_color.z;

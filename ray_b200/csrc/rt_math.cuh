@@ -453,6 +453,157 @@ RT_FN float libm_expf(float x) {
     return float(y);
 }
 
+// logf and powf of the host libm (glibc 2.39 sysdeps/ieee754/flt-32/e_logf.c, e_powf.c: the Arm optimized-routines
+// algorithms -- a 16-entry {1/c, log(c)} table indexed by the top mantissa bits, a short polynomial in double precision,
+// for powf followed by the exp2 kernel of libm_expf).  The reference calls logf in D_GTR1 (clearcoat lobe,
+// ShadeRef.cpp) and powf in the display transform (TonemapRef.h:20-47: the sRGB OETF and 1/gamma), so with these the
+// tonemapped plane and the clearcoat pdf are the host's floats, not CUDA's <= 2 ulp versions.  Table values are the
+// published constants of those files as found in this image's libm.so.6; tests/test_libm.py compares tens of millions of
+// arguments with the host functions.
+struct LibmLogTab {
+    double invc, logc;
+};
+RT_FN float libm_logf(float x) {
+    static const LibmLogTab T[16] = {
+        {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2},
+        {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+        {0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2},
+        {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+        {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3},
+        {0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3},
+        {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4},
+        {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+        {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5},
+        {0x1.0000000000000p+0, 0x0.0p+0},
+        {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},
+        {0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4},
+        {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},
+        {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3},
+        {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},
+        {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+    const double Ln2 = 0x1.62e42fefa39efp-1, A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) {
+        return 0.0f;
+    }
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        // x < 0x1p-126 or inf or nan
+        if (ix * 2 == 0) {
+            return -__uint_as_float(0x7f800000u); // log(+-0) = -inf
+        }
+        if (ix == 0x7f800000u) {
+            return x; // log(inf) = inf
+        }
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) {
+            return __uint_as_float(0x7fc00000u) ; // log(negative) / log(nan)
+        }
+        // subnormal: normalise
+        ix = __float_as_uint(x * 0x1p23f);
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = int((tmp >> (23 - 4)) % 16u);
+    const int k = int(tmp) >> 23; // arithmetic shift
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double invc = T[i].invc, logc = T[i].logc;
+    const double z = double(__uint_as_float(iz));
+    const double r = z * invc - 1;
+    const double y0 = logc + double(k) * Ln2;
+    const double r2 = r * r;
+    double y = A1 * r + A2;
+    y = A0 * r2 + y;
+    y = y * r2 + (y0 + r);
+    return float(y);
+}
+
+// x > 0 finite or x == 0, y finite: the calls the display transform makes (x = a linear pixel value, y = 1/2.4 or
+// 1/gamma).  Negative x (a non-integer power is NaN), infinities and NaNs take the device powf: they never reach a
+// comparable pixel.
+RT_FN float libm_powf(float x, float y) {
+    static const LibmLogTab T[16] = {
+        {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2},
+        {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},
+        {0x1.49539f0f010b0p+0, -0x1.7418b0a1fb77bp-2},
+        {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},
+        {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2},
+        {0x1.25e227b0b8ea0p+0, -0x1.97c1d1b3b7af0p-3},
+        {0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3},
+        {0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4},
+        {0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5},
+        {0x1.0000000000000p+0, 0x0.0p+0},
+        {0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4},
+        {0x1.ca4b31f026aa0p-1, 0x1.476a9543891bap-3},
+        {0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3},
+        {0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2},
+        {0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2},
+        {0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2}};
+    const double P0 = 0x1.27616c9496e0bp-2, P1 = -0x1.71969a075c67ap-2, P2 = 0x1.ec70a6ca7baddp-2, P3 = -0x1.7154748bef6c8p-1,
+                 P4 = 0x1.71547652ab82bp+0;
+    static const uint64_t E[32] = {0x3ff0000000000000ULL,0x3fefd9b0d3158574ULL,0x3fefb5586cf9890fULL,0x3fef9301d0125b51ULL,0x3fef72b83c7d517bULL,0x3fef54873168b9aaULL,0x3fef387a6e756238ULL,0x3fef1e9df51fdee1ULL,0x3fef06fe0a31b715ULL,0x3feef1a7373aa9cbULL,0x3feedea64c123422ULL,0x3feece086061892dULL,0x3feebfdad5362a27ULL,0x3feeb42b569d4f82ULL,0x3feeab07dd485429ULL,0x3feea47eb03a5585ULL,0x3feea09e667f3bcdULL,0x3fee9f75e8ec5f74ULL,0x3feea11473eb0187ULL,0x3feea589994cce13ULL,0x3feeace5422aa0dbULL,0x3feeb737b0cdc5e5ULL,0x3feec49182a3f090ULL,0x3feed503b23e255dULL,0x3feee89f995ad3adULL,0x3feeff76f2fb5e47ULL,0x3fef199bdd85529cULL,0x3fef3720dcef9069ULL,0x3fef5818dcfba487ULL,0x3fef7c97337b9b5fULL,0x3fefa4afa2a490daULL,0x3fefd0765b6e4540ULL};
+    const double SHIFT = 0x1.8p+52 / 32, C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
+    uint32_t ix = __float_as_uint(x);
+    const uint32_t iy = __float_as_uint(y);
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u || (iy * 2 - 1 >= 2u * 0x7f800000u - 1)) {
+        if (iy * 2 == 0) {
+            return 1.0f; // x^0
+        }
+        if (ix == 0x3f800000u) {
+            return 1.0f;
+        }
+        if (ix * 2 == 0 && iy * 2 < 2u * 0x7f800000u) {
+            return (iy & 0x80000000u) ? __uint_as_float(0x7f800000u) : 0.0f; // (+-0)^y, y non-integer sign ignored: |result|
+        }
+        if ((ix & 0x80000000u) || ix >= 0x7f800000u || iy * 2 >= 2u * 0x7f800000u) {
+            return powf(x, y); // negative base / inf / nan: off the compared path
+        }
+        // subnormal x: normalise
+        ix = __float_as_uint(x * 0x1p23f);
+        ix &= 0x7fffffffu;
+        ix -= 23u << 23;
+    }
+    // log2_inline
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = int((tmp >> (23 - 4)) % 16u);
+    const uint32_t top = tmp & 0xff800000u;
+    const uint32_t iz = ix - top;
+    const int k = int(tmp) >> 23;
+    const double invc = T[i].invc, logc = T[i].logc;
+    const double z = double(__uint_as_float(iz));
+    const double r = z * invc - 1;
+    const double y0 = logc + double(k);
+    const double r2 = r * r;
+    double yy = P0 * r + P1;
+    const double p = P2 * r + P3;
+    const double r4 = r2 * r2;
+    double q = P4 * r + y0;
+    q = p * r2 + q;
+    yy = yy * r4 + q;
+    const double ylogx = double(y) * yy;
+    if (((uint64_t(__double_as_longlong(ylogx)) >> 47) & 0xffffu) >= (uint64_t(__double_as_longlong(126.0)) >> 47)) {
+        // |y * log2(x)| >= 126
+        if (ylogx > 0x1.fffffffd1d571p+6) {
+            return __uint_as_float(0x7f800000u);
+        }
+        if (ylogx <= -150.0) {
+            return 0.0f;
+        }
+    }
+    // exp2_inline
+    double kd = ylogx + SHIFT;
+    const uint64_t ki = uint64_t(__double_as_longlong(kd));
+    kd -= SHIFT;
+    const double rr = ylogx - kd;
+    uint64_t t = E[ki % 32];
+    t += ki << (52 - 5);
+    const double s = __longlong_as_double((long long)t);
+    const double zz = C0 * rr + C1;
+    const double rr2 = rr * rr;
+    double o = C2 * rr + 1;
+    o = zz * rr2 + o;
+    o = o * s;
+    return float(o);
+}
+
 // exp2f(float(e) - 128.0f) of rgbe_to_rgb (CoreRef.h:234-237): an exact power of two for every byte e
 RT_DEV float rgbe_scale(uint32_t e) {
     const int n = int(e) - 128;

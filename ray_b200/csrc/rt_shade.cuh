@@ -169,7 +169,7 @@ RT_DEV float D_GTR1(float NDotH, float a) {
     const float a2 = sqr(a);
     const float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
     // NOTE: the reference calls libm logf here; CUDA's logf may differ from glibc's by 1 ulp (clearcoat lobe only)
-    return (a2 - 1.0f) / (kPi * logf(a2) * t);
+    return (a2 - 1.0f) / (kPi * libm_logf(a2) * t);
 }
 
 RT_FN float D_GGX(v3 H, v2 alpha) {
@@ -1192,7 +1192,7 @@ RT_DEV bool shade_surface_a(const bool tex_on, const PassSettings &ps, float lim
         float mix_val = mat->tangent_rotation_or_strength;
         const uint32_t mix_texture = mat->textures[kTexBase];
         if (tex_on && mix_texture != kTexInvalid) {
-            mix_val *= tex_sample_color(sc.tex, mix_texture, surf.uvs, 0, tex_rand).x;
+            mix_val *= tex_sample_color(sc.tex, mix_texture, surf.uvs, 0, tex_rand, true).x;
         }
         const float eta = is_backfacing ? safe_div_pos(ext_ior, mat->ior) : safe_div_pos(mat->ior, ext_ior);
         const float RR = mat->ior != 0.0f ? fresnel_dielectric_cos(dot(I, surf.N), eta) : 1.0f;
@@ -1324,7 +1324,7 @@ RT_DEV void shade_surface_b(const bool tex_on, MatCtx &c, float limit1, ShadeOut
     v3 base_color = mk3(mat->base_color);
     if (tex_on && mat->textures[kTexBase] != kTexInvalid) { // ShadeRef.cpp:1405-1419
         const uint32_t base_texture = mat->textures[kTexBase];
-        const c4 tex_color = tex_sample_color(sc.tex, base_texture, surf.uvs, tex_lod(sc.tex, base_texture, c.lambda), c.tex_rand);
+        const c4 tex_color = tex_sample_color(sc.tex, base_texture, surf.uvs, tex_lod(sc.tex, base_texture, c.lambda), c.tex_rand, true);
         base_color.x *= tex_color.x;
         base_color.y *= tex_color.y;
         base_color.z *= tex_color.z;

@@ -61,9 +61,39 @@ RT_DEV c4 tex_unpack(uint32_t px) { // color_rgba_t of Fetch(): byte / 255.0f
               float(px >> 24) / 255.0f};
 }
 
-// fvec4 colour of a texture sample after the handle's colour-space flag (YCoCg handles are rejected at upload)
-RT_DEV c4 tex_sample_color(const SceneTex &t, uint32_t handle, v2 uvs, int lod, v2 rand) {
+// YCoCg_to_RGB (CoreRef.h:239-251): the scaled YCoCg the reference stores base-colour maps in when texture compression is
+// on (decoded BC3 texels cross the C-ABI: {Co, Cg, scale, Y})
+RT_DEV c4 ycocg_to_rgb(c4 col) {
+    const float scale = (col.z * (255.0f / 8.0f)) + 1.0f;
+    const float Y = col.w;
+    const float Co = (col.x - (0.5f * 256.0f / 255.0f)) / scale;
+    const float Cg = (col.y - (0.5f * 256.0f / 255.0f)) / scale;
+    c4 rgb;
+    rgb.x = sse_max(0.0f, sse_min(Y + Co - Cg, 1.0f));
+    rgb.y = sse_max(0.0f, sse_min(Y + Cg, 1.0f));
+    rgb.z = sse_max(0.0f, sse_min(Y - Co - Cg, 1.0f));
+    rgb.w = 1.0f;
+    return rgb;
+}
+
+RT_DEV float srgb_to_linear_f(float c) { // CoreRef.h:208-220 on a float (after YCoCg the value is no longer a byte / 255)
+    return (c > 0.04045f) ? libm_powf((c + 0.055f) / 1.055f, 2.4f) : (c / 12.92f);
+}
+
+// fvec4 colour of a texture sample after the handle's colour-space flags.  `ycocg`: the call site is one of those where
+// the reference converts YCoCg-coded texels (base colour, texture-driven Mix, textured emissive triangles:
+// ShadeRef.cpp:1308,1411, CoreRef.cpp:3108,3232,3567); the other sites (roughness, specular ...) read the raw channels.
+RT_DEV c4 tex_sample_color(const SceneTex &t, uint32_t handle, v2 uvs, int lod, v2 rand, bool ycocg = false) {
     const uint32_t px = tex_sample_bytes(t, handle, uvs, lod, rand);
+    if (ycocg && (handle & kTexYCoCgBit)) {
+        c4 col = ycocg_to_rgb(tex_unpack(px));
+        if (handle & kTexSrgbBit) {
+            col.x = srgb_to_linear_f(col.x);
+            col.y = srgb_to_linear_f(col.y);
+            col.z = srgb_to_linear_f(col.z);
+        }
+        return col;
+    }
     if (handle & kTexSrgbBit) {
         return c4{__ldg(&t.srgb_lut[px & 0xffu]), __ldg(&t.srgb_lut[(px >> 8) & 0xffu]),
                   __ldg(&t.srgb_lut[(px >> 16) & 0xffu]), float(px >> 24) / 255.0f};

@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_BLOCKS)
                         float mix_val = mat->tangent_rotation_or_strength;
                         const uint32_t mix_texture = mat->textures[kTexBase];
                         if (mix_texture != kTexInvalid) {
-                            mix_val *= tex_sample_color(p.sc.tex, mix_texture, uvs, 0, tex_rand).x;
+                            mix_val *= tex_sample_color(p.sc.tex, mix_texture, uvs, 0, tex_rand, true).x;
                         }
                         if (trans_r > mix_val) {
                             mat = &p.sc.surf.materials[mat->textures[kMixMat1]];
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_BLOCKS)
                             float mix_val = mat->tangent_rotation_or_strength;
                             const uint32_t mix_texture = mat->textures[kTexBase];
                             if (mix_texture != kTexInvalid) {
-                                mix_val *= tex_sample_color(p.sc.tex, mix_texture, sh_uvs, 0, tex_rand).x;
+                                mix_val *= tex_sample_color(p.sc.tex, mix_texture, sh_uvs, 0, tex_rand, true).x;
                             }
                             mstack[ms] = mat->textures[kMixMat1];
                             wstack[ms++] = weight * (1.0f - mix_val);

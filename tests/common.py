@@ -7,11 +7,11 @@ from ray_b200 import capi, cuda, scenes
 class Pair:
     """Oracle scene (reference Cpu::Scene, wide BVH) + CUDA context holding byte-identical arrays (oracle mode 1b)."""
 
-    def __init__(self, oracle, desc, device=0):
+    def __init__(self, oracle, desc, device=0, tex_compression=False):
         self.oracle = oracle
         self.desc = desc
         self.w, self.h = desc.width, desc.height
-        self.osc = scenes.build(desc, oracle.Scene(wide=True))
+        self.osc = scenes.build(desc, oracle.Scene(wide=True, tex_compression=tex_compression))
         self.cam = self.osc.camera()
         self.ctx = cuda.Context(device)
         self.ctx.resize(self.w, self.h)

@@ -34,6 +34,7 @@ def load():
         "ro_set_verbose": (None, [C.c_int]),
         "ro_cpu_features": (C.c_int, []),
         "ro_scene_create": (vp, [C.c_int]),
+        "ro_scene_create_ex": (vp, [C.c_int, C.c_int]),
         "ro_scene_destroy": (None, [vp]),
         "ro_add_texture": (C.c_uint32, [vp, P(capi.rs_tex_desc)]),
         "ro_add_material_node": (C.c_uint32, [vp, P(capi.rs_shading_node_desc)]),
@@ -96,9 +97,9 @@ def _ptr(a):
 class Scene:
     """The reference's Cpu::Scene(use_wide_bvh) behind the scene-building verbs of ray_b200.scenes.build()."""
 
-    def __init__(self, wide=True):
+    def __init__(self, wide=True, tex_compression=False):
         self.lib = load()
-        self.h = self.lib.ro_scene_create(1 if wide else 0)
+        self.h = self.lib.ro_scene_create_ex(1 if wide else 0, 1 if tex_compression else 0)
         self._keep = []
 
     def close(self):

@@ -126,3 +126,52 @@ int main(void){ long bad=0;
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     sys.stdout.write(out.stdout)
     assert out.returncode == 0, out.stdout
+
+
+def test_device_logf_powf_restatements_match_host_libm(tmp_path):
+    """libm_logf (D_GTR1 of the clearcoat lobe) and libm_powf (sRGB OETF / 1/gamma of the display transform), compiled as
+    C, against the host logf / powf on the argument ranges the path produces plus edge cases."""
+    src = open(os.path.join(ROOT, "ray_b200", "csrc", "rt_math.cuh")).read()
+    i0 = src.index("struct LibmLogTab {")
+    i1 = src.index("// exp2f(float(e) - 128.0f) of rgbe_to_rgb")
+    code = src[i0:i1].replace("RT_FN", "static")
+    c = r'''
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+static inline uint32_t __float_as_uint(float f){uint32_t i;memcpy(&i,&f,4);return i;}
+static inline float __uint_as_float(uint32_t i){float f;memcpy(&f,&i,4);return f;}
+static inline long long __double_as_longlong(double d){long long i;memcpy(&i,&d,8);return i;}
+static inline double __longlong_as_double(long long i){double d;memcpy(&d,&i,8);return d;}
+#define double(x) ((double)(x))
+#define float(x) ((float)(x))
+#define int(x) ((int)(x))
+#define uint64_t(x) ((uint64_t)(x))
+typedef struct LibmLogTab LibmLogTab;
+''' + code + r'''
+static uint32_t rng=4242; static uint32_t r32(void){ rng^=rng<<13; rng^=rng>>17; rng^=rng<<5; return rng; }
+static double u01(void){ return (double)r32()/4294967296.0; }
+static int same(float a, float b){ return __float_as_uint(a)==__float_as_uint(b) || (a!=a && b!=b); }
+int main(void){ long bad=0;
+  const float ys[] = {1.0f/2.4f, 1.0f/2.2f, 2.4f, 0.5f, 1.0f/1.8f, 3.0f, 0.45f};
+  for(long i=0;i<12000000;i++){
+    float x = (float)(u01()*1.2); if((i&7)==1) x = (float)(u01()*64.0); if((i&7)==2) x = __uint_as_float(r32() & 0x7f7fffffu);
+    float y = ys[i % 7]; volatile float xv=x, yv=y;
+    if(!same(powf(xv,yv), libm_powf(x,y))){ if(bad<5)printf("powf %a %a: %a %a\n",x,y,powf(xv,yv),libm_powf(x,y)); bad++; }
+    float l = (float)(u01()*4.0); if((i&3)==1) l = __uint_as_float(r32() & 0x7f7fffffu);
+    volatile float lv=l;
+    if(!same(logf(lv), libm_logf(l))){ if(bad<5)printf("logf %a: %a %a\n",l,logf(lv),libm_logf(l)); bad++; } }
+  const float e[]={0.0f,1.0f,0x1p-126f,0x1p-127f,0x1p-149f,0.0031308f,1e-30f,1e30f,3.4e38f,0.99999994f,1.0000001f,2.0f,0.5f};
+  for(unsigned i=0;i<sizeof(e)/sizeof(e[0]);i++) for(unsigned j=0;j<7;j++){ volatile float a=e[i], b=ys[j];
+    if(!same(powf(a,b), libm_powf(e[i],ys[j]))){ printf("powf edge %a %a\n",e[i],ys[j]); bad++; }
+    if(j==0 && !same(logf(a), libm_logf(e[i]))){ printf("logf edge %a\n",e[i]); bad++; } }
+  printf("bad=%ld\n",bad); return bad!=0; }
+'''
+    f = tmp_path / "powf.c"
+    f.write_text(c)
+    exe = tmp_path / "powf"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(f), "-lm"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    sys.stdout.write(out.stdout)
+    assert out.returncode == 0, out.stdout
