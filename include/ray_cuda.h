@@ -159,6 +159,25 @@ int rc_sync(rc_ctx *ctx);
  * linear image to RC_BUF_RAW and its tonemapped version to RC_BUF_FINAL, updates required-samples.  Uses the variance
  * threshold and gamma of the last rc_render; `iteration` = RegionContext::iteration.  Blocking. */
 int rc_denoise_nlm(rc_ctx *ctx, const rc_rect *rect, int iteration);
+/* RendererBase::DenoiseImage(int pass, const RegionContext &) / InitUNetFilter (internal/RendererCPU.h:790-1007,
+ * :1261-1279): the 16-pass UNet denoiser over the accumulated colour, base-colour and normal planes.
+ * rc_unet_set_weights: the 16 convolutions in pass order (enc_conv0, enc_conv1..4, enc_conv5a, enc_conv5b, dec_conv4a,
+ *   dec_conv4b, dec_conv3a, dec_conv3b, dec_conv2a, dec_conv2b, dec_conv1a, dec_conv1b, dec_conv0), each as fp16 OIHW
+ *   weights [cout][cin][3][3] + fp16 biases [cout] -- the layout of OIDN's weight blobs the reference embeds
+ *   (internal/precomputed/__oidn_weights_hdr_alb_nrm.inl).  Channel counts are checked against the network's shape.
+ * rc_denoise_unet: pass 0..15 runs that pass over `rect` (frame coordinates; passes < 15 round it up to a multiple of
+ *   16 like the reference), pass -1 runs all 16.  Pass 15 writes the filtered linear image to RC_BUF_RAW and its
+ *   tonemapped version to RC_BUF_FINAL.  flags: RC_UNET_TENSOR_CORES (default path) computes the convolutions in fp16
+ *   on the tensor cores with fp32 accumulation, RC_UNET_FP32 in fp32 FFMA (the parity anchor).  Blocking. */
+typedef struct rc_unet_layer {
+    const uint16_t *weights; /* fp16 bits, cout * cin * 9 */
+    const uint16_t *bias;    /* fp16 bits, cout */
+    int32_t cin, cout;
+} rc_unet_layer;
+enum { RC_UNET_TENSOR_CORES = 0, RC_UNET_FP32 = 1 };
+int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]);
+int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags);
+
 /* dst: rect.w*rect.h RGBA float pixels written with the given pitch (in pixels). */
 int rc_readback(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch);
 int rc_readback_required_samples(rc_ctx *ctx, uint16_t *dst);

@@ -27,6 +27,9 @@ rh_renderer *rh_create_renderer(int w, int h, int device);
  * the frame is sharded over them in row bands (rc_comm_* of ray_cuda.h) */
 rh_renderer *rh_create_renderer_multi(int w, int h, const char *devices);
 int rh_device_count(rh_renderer *r);
+/* UNet denoiser (RendererBase::InitUNetFilter + DenoiseImage(pass, region) x pass_count): weights as rc_unet_layer[16] */
+int rh_set_unet_weights(rh_renderer *r, const rc_unet_layer layers[16], uint32_t unet_flags);
+int rh_denoise_unet(rh_renderer *r, const rc_rect *rect, int iteration);
 void rh_destroy_renderer(rh_renderer *r);
 const char *rh_device_name(rh_renderer *r);
 int rh_error_count(rh_renderer *r);

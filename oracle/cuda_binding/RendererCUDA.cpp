@@ -21,6 +21,9 @@
 #include "../../include/ray_cuda.h"
 
 namespace Ray {
+namespace oidn_hdr_alb_nrm { // the weight set of the reference's UNet filter (UNetFilter.cpp:13-15), from where it lies
+#include "internal/precomputed/__oidn_weights_hdr_alb_nrm.inl"
+}
 extern const uint32_t __pmj02_samples[]; // internal/precomputed/__pmj02_samples.inl through Core.cpp
 namespace Cuda {
 // the enumerator a maintainer appends to eRendererType (RendererBase.h:22-34); the unmodified header ends at DirectX12 = 7
@@ -332,7 +335,13 @@ class Renderer final : public RendererBase {
         }
         final_dirty_ = raw_dirty_ = true;
     }
-    void DenoiseImage(int, const RegionContext &) override { log_->Error("Ray(CUDA): UNet denoising is not implemented"); }
+    void DenoiseImage(const int pass, const RegionContext &region) override { // UNet overload, RendererCPU.h:790-1007
+        const rc_rect r = {region.rect().x, region.rect().y, region.rect().w, region.rect().h};
+        if (rc_denoise_unet(ctx_, pass, &r, RC_UNET_TENSOR_CORES) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+        }
+        final_dirty_ = raw_dirty_ = true;
+    }
     void UpdateSpatialCache(const SceneBase &, RegionContext &) override { log_->Error("Ray(CUDA): no spatial cache"); }
     void ResolveSpatialCache(const SceneBase &, const std::function<void(int, int, ParallelForFunction &&)> &) override {
         log_->Error("Ray(CUDA): no spatial cache");
@@ -355,8 +364,26 @@ class Renderer final : public RendererBase {
     }
     void ResetStats() override { rc_reset_stats(ctx_); }
     unet_filter_properties_t InitUNetFilter(bool, const std::function<void(int, int, ParallelForFunction &&)> &) override {
-        log_->Error("Ray(CUDA): the UNet filter is not implemented");
-        return {};
+        using namespace oidn_hdr_alb_nrm;
+#define RC_L(n, ci, co) rc_unet_layer{n##_weight, n##_bias, ci, co}
+        const rc_unet_layer layers[16] = {
+            RC_L(enc_conv0, 9, 32),     RC_L(enc_conv1, 32, 32),   RC_L(enc_conv2, 32, 48),    RC_L(enc_conv3, 48, 64),
+            RC_L(enc_conv4, 64, 80),    RC_L(enc_conv5a, 80, 96),  RC_L(enc_conv5b, 96, 96),   RC_L(dec_conv4a, 160, 112),
+            RC_L(dec_conv4b, 112, 112), RC_L(dec_conv3a, 160, 96), RC_L(dec_conv3b, 96, 96),   RC_L(dec_conv2a, 128, 64),
+            RC_L(dec_conv2b, 64, 64),   RC_L(dec_conv1a, 73, 64),  RC_L(dec_conv1b, 64, 32),   RC_L(dec_conv0, 32, 3)};
+#undef RC_L
+        unet_filter_properties_t props = {};
+        if (rc_unet_set_weights(ctx_, layers) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+            return props;
+        }
+        props.pass_count = 16; // UNetFilterPasses; tensors are not aliased on the device: no inter-pass dependencies to report
+        for (int i = 0; i < 16; ++i) {
+            for (int j = 0; j < 4; ++j) {
+                props.alias_dependencies[i][j] = -1;
+            }
+        }
+        return props;
     }
 };
 

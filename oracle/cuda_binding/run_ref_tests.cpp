@@ -29,7 +29,7 @@
     X(complex_mat5) X(complex_mat5_clipped) X(complex_mat5_adaptive) X(complex_mat5_regions) X(complex_mat5_nlm_filter) \
     X(complex_mat5_dof) X(complex_mat5_mesh_lights) X(complex_mat5_sphere_light) X(complex_mat5_inside_light)          \
     X(complex_mat5_spot_light) X(complex_mat5_hdri_light) X(two_sided_mat) X(aux_channels)
-// needs the UNet denoiser (RendererBase::DenoiseImage(pass, region)): listed, not part of a group yet
+// the UNet denoiser (RendererBase::DenoiseImage(pass, region)); complex_mat5_dir_light is parked here too (see below)
 // complex_mat5_dir_light renders through a filmic (LUT) view transform, which this backend does not implement yet
 #define UNET(X) X(ray_flags) X(complex_mat5_unet_filter) X(complex_mat5_dir_light)
 UNTEXTURED(T)

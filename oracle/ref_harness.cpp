@@ -40,6 +40,12 @@
 
 using namespace Ray;
 
+// the OIDN weight set the reference's UNet filter uses (Apache-2.0 data file of the reference tree, included from where
+// it lies): handed to the CUDA backend through rc_unet_set_weights by the parity tests
+namespace oidn_hdr_alb_nrm {
+#include "internal/precomputed/__oidn_weights_hdr_alb_nrm.inl"
+}
+
 namespace {
 
 class CountingLog final : public ILog {
@@ -944,6 +950,37 @@ void ro_view_render_sample(const rc_scene_view *v, const rc_camera *cam, ro_scen
         rays_out[0] += n_rays.load();
         rays_out[1] += n_shadow.load();
     }
+}
+
+// RendererBase::InitUNetFilter + DenoiseImage(pass, region) for every pass over `rect` (the UNet overload)
+int ro_denoise_unet(ro_renderer *r, const rc_rect *rect, int iteration) {
+    RendererBase *rb = reinterpret_cast<OracleRenderer *>(r)->r.get();
+    const unet_filter_properties_t props = rb->InitUNetFilter(false, parallel_for_serial);
+    RegionContext region(rect_t{rect->x, rect->y, rect->w, rect->h});
+    region.iteration = iteration;
+    for (int pass = 0; pass < props.pass_count; ++pass) {
+        rb->DenoiseImage(pass, region);
+    }
+    return props.pass_count;
+}
+
+// layer i (pass order) of the reference's UNet weight set: fp16 OIHW weights + fp16 biases
+void ro_unet_layer(int i, const uint16_t **weights, int *weights_count, const uint16_t **bias, int *bias_count) {
+    using namespace oidn_hdr_alb_nrm;
+#define RO_L(n) {n##_weight, int(sizeof(n##_weight) / 2), n##_bias, int(sizeof(n##_bias) / 2)}
+    static const struct {
+        const uint16_t *w;
+        int wn;
+        const uint16_t *b;
+        int bn;
+    } L[16] = {RO_L(enc_conv0),  RO_L(enc_conv1),  RO_L(enc_conv2),  RO_L(enc_conv3),  RO_L(enc_conv4), RO_L(enc_conv5a),
+               RO_L(enc_conv5b), RO_L(dec_conv4a), RO_L(dec_conv4b), RO_L(dec_conv3a), RO_L(dec_conv3b), RO_L(dec_conv2a),
+               RO_L(dec_conv2b), RO_L(dec_conv1a), RO_L(dec_conv1b), RO_L(dec_conv0)};
+#undef RO_L
+    *weights = L[i].w;
+    *weights_count = L[i].wn;
+    *bias = L[i].b;
+    *bias_count = L[i].bn;
 }
 
 } // extern "C"

@@ -204,6 +204,7 @@ class rc_counters(C.Structure):
 
 
 RC_RENDER_ASYNC, RC_RENDER_NO_SORT = 1, 2
+RC_UNET_TENSOR_CORES, RC_UNET_FP32 = 0, 1
 RC_BUF_FINAL, RC_BUF_RAW, RC_BUF_BASE_COLOR, RC_BUF_DEPTH_NORMALS, RC_BUF_FULL, RC_BUF_HALF, RC_BUF_TEMP = range(7)
 
 

@@ -361,13 +361,47 @@ void Renderer::DenoiseImage(const RegionContext &region) {
     }
     final_dirty_ = raw_dirty_ = true;
 }
-void Renderer::DenoiseImage(int, const RegionContext &) { log_->Error("Ray(CUDA): UNet denoising is not implemented by the CUDA backend"); }
+// reference internal/RendererCPU.h:790-1007: one pass of the 16-pass UNet filter (rt_unet.cuh)
+void Renderer::DenoiseImage(const int pass, const RegionContext &region) {
+    if (comm_) {
+        log_->Error("Ray(CUDA): the UNet filter is not available on a multi-device renderer yet");
+        return;
+    }
+    const rect_t &r = region.rect();
+    const rc_rect rr = {r.x, r.y, r.w, r.h};
+    if (rc_denoise_unet(ctx_, pass, &rr, unet_flags_) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+        return;
+    }
+    final_dirty_ = raw_dirty_ = true;
+}
 void Renderer::UpdateSpatialCache(const SceneBase &, RegionContext &) { log_->Error("Ray(CUDA): the spatial cache is not implemented by the CUDA backend"); }
 void Renderer::ResolveSpatialCache(const SceneBase &, const ParallelFor &) { log_->Error("Ray(CUDA): the spatial cache is not implemented by the CUDA backend"); }
 void Renderer::ResetSpatialCache(const SceneBase &, const ParallelFor &) {}
+// The stand-alone library does not carry OIDN's weight blob (inside the reference tree the binding passes the tree's
+// own, oracle/cuda_binding/RendererCUDA.cpp): the application hands it over once with SetUNetWeights.
+bool Renderer::SetUNetWeights(const rc_unet_layer layers[16]) {
+    if (rc_unet_set_weights(ctx_, layers) != 0) {
+        log_->Error("Ray(CUDA): %s", rc_last_error(ctx_));
+        return false;
+    }
+    unet_weights_set_ = true;
+    return true;
+}
+
 unet_filter_properties_t Renderer::InitUNetFilter(bool, const ParallelFor &) {
-    log_->Error("Ray(CUDA): the UNet filter is not implemented by the CUDA backend");
-    return {};
+    unet_filter_properties_t props = {};
+    if (!unet_weights_set_) {
+        log_->Error("Ray(CUDA): InitUNetFilter needs the network weights (Cuda::Renderer::SetUNetWeights)");
+        return props;
+    }
+    props.pass_count = 16; // UNetFilterPasses
+    for (int i = 0; i < 16; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            props.alias_dependencies[i][j] = -1; // tensors are not aliased on the device
+        }
+    }
+    return props;
 }
 
 void Renderer::GetStats(stats_t &st) {

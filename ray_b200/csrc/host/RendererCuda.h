@@ -38,6 +38,8 @@ class Renderer final : public RendererBase {
     bool tables_dirty_ = true;
     std::vector<float> filter_table_;
     uint32_t render_flags_ = 0;
+    uint32_t unet_flags_ = RC_UNET_TENSOR_CORES;
+    bool unet_weights_set_ = false;
 
     void Readback(int which, color_rgba_t *dst) const;
     void FreeMirrors();
@@ -76,6 +78,9 @@ class Renderer final : public RendererBase {
     /// reference tree this is `__pmj02_samples`; parity tests pass that table so the sample sequences are identical.
     void SetSamplerTable(const uint32_t *table);
     void SetRenderFlags(uint32_t rc_render_flags) { render_flags_ = rc_render_flags; }
+    /// The 16 convolutions of the UNet denoiser as fp16 OIHW weights + biases (include/ray_cuda.h rc_unet_layer).
+    bool SetUNetWeights(const rc_unet_layer layers[16]);
+    void SetUNetFlags(uint32_t rc_unet_flags) { unet_flags_ = rc_unet_flags; }
     /// Forget the uploaded scene: the next RenderScene copies all scene arrays host->device again (dynamic scenes,
     /// end-to-end measurements).
     void InvalidateScene() { uploaded_scene_ = nullptr; }

@@ -161,6 +161,20 @@ void rh_get_counters(rh_renderer *r, rc_counters *out) {
     }
 }
 int rh_device_count(rh_renderer *r) { return R(r)->device_count(); }
+// UNet denoiser: weights once, then InitUNetFilter + DenoiseImage(pass, region) for every pass (returns the pass count)
+int rh_set_unet_weights(rh_renderer *r, const rc_unet_layer layers[16], uint32_t unet_flags) {
+    R(r)->SetUNetFlags(unet_flags);
+    return R(r)->SetUNetWeights(layers) ? 0 : 1;
+}
+int rh_denoise_unet(rh_renderer *r, const rc_rect *rect, int iteration) {
+    const unet_filter_properties_t props = R(r)->InitUNetFilter(false, parallel_for_serial);
+    RegionContext region(rect_t{rect->x, rect->y, rect->w, rect->h});
+    region.iteration = iteration;
+    for (int pass = 0; pass < props.pass_count; ++pass) {
+        R(r)->DenoiseImage(pass, region);
+    }
+    return props.pass_count;
+}
 void rh_get_kernel_ms(rh_renderer *r, double ms[6], uint64_t launches[6]) { rc_get_kernel_ms(R(r)->native_context(), ms, launches); }
 void rh_set_sampler_table(rh_renderer *r, const uint32_t *table) { R(r)->SetSamplerTable(table); }
 void rh_set_render_flags(rh_renderer *r, uint32_t f) { R(r)->SetRenderFlags(f); }

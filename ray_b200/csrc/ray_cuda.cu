@@ -21,6 +21,7 @@
 #include "rt_trace.cuh"
 #include "rt_sort.cuh"
 #include "rt_denoise.cuh"
+#include "rt_unet.cuh"
 
 using namespace rt;
 
@@ -67,6 +68,11 @@ struct rc_ctx {
     DevArray dnodes, blas_roots, dmtris; // device-built traversal copies (rt_trace.cuh)
     uint32_t tlas_root_word = kEmptyChild;
     int trace_fin_min = 32;         // lanes of a warp that must have finished before their epilogue + refill is issued
+    // UNet denoiser (rt_unet.cuh): weights as uploaded + the 15 intermediate tensors of the current frame size
+    float *unet_w[kUNetLayers] = {}, *unet_b[kUNetLayers] = {};
+    float *unet_t[15] = {};
+    int unet_tw = 0, unet_th = 0; // rounded frame the tensors were sized for
+    bool unet_ready = false;
     float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
     size_t nlm_scratch_elems = 0;
     float last_inv_gamma = 1.0f, last_variance_threshold = 0.0f; // tonemap_params_ / variance_threshold_ of the reference
@@ -841,6 +847,13 @@ void rc_destroy(rc_ctx *ctx) {
     cudaFree(ctx->d_filter_table);
     cudaFree(ctx->d_srgb_lut);
     cudaFree(ctx->nlm_scratch);
+    for (int i = 0; i < kUNetLayers; ++i) {
+        cudaFree(ctx->unet_w[i]);
+        cudaFree(ctx->unet_b[i]);
+    }
+    for (float *t : ctx->unet_t) {
+        cudaFree(t);
+    }
     for (DevArray *a : {&ctx->dnodes, &ctx->blas_roots, &ctx->dmtris, &ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
                         &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {
@@ -1164,6 +1177,174 @@ int rc_render(rc_ctx *ctx, const rc_pass_desc *pass) {
     }
     if ((pass->flags & RC_RENDER_ASYNC) == 0) {
         return rc_sync(ctx);
+    }
+    return 0;
+}
+
+// ---- UNet denoiser (rt_unet.cuh) ----------------------------------------------------------------------------------
+namespace {
+float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = uint32_t(h & 0x8000u) << 16, exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else { // subnormal
+            int e = -1;
+            uint32_t m = man;
+            do {
+                ++e;
+                m <<= 1;
+            } while ((m & 0x400u) == 0);
+            bits = sign | uint32_t(127 - 15 - e) << 23 | (m & 0x3ffu) << 13;
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | man << 13;
+    } else {
+        bits = sign | (exp + 127 - 15) << 23 | man << 13;
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+// tensor i of the network (output of pass i, i < 15): channels and down-scale shift
+void unet_tensor_shape(int i, int &channels, int &shift) {
+    const UNetLayerShape L = unet_layer(i);
+    channels = L.cout;
+    shift = L.level + (L.pool ? 1 : 0);
+}
+
+int unet_alloc_tensors(rc_ctx *ctx) {
+    const int wr = (ctx->w + 15) / 16 * 16, hr = (ctx->h + 15) / 16 * 16;
+    if (ctx->unet_tw == wr && ctx->unet_th == hr && ctx->unet_t[0]) {
+        return 0;
+    }
+    for (float *&t : ctx->unet_t) {
+        cudaFree(t);
+        t = nullptr;
+    }
+    ctx->unet_tw = ctx->unet_th = 0;
+    for (int i = 0; i < 15; ++i) {
+        int c, sh;
+        unet_tensor_shape(i, c, sh);
+        const size_t n = size_t(wr >> sh) * size_t(hr >> sh) * size_t(c);
+        CU_CHECK(ctx, cudaMalloc(&ctx->unet_t[i], (n ? n : 1) * sizeof(float)));
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->unet_t[i], 0, (n ? n : 1) * sizeof(float), ctx->stream));
+    }
+    ctx->unet_tw = wr;
+    ctx->unet_th = hr;
+    return 0;
+}
+} // namespace
+
+int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]) {
+    if (!ctx || !layers) {
+        return fail(ctx, "rc_unet_set_weights: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    ctx->unet_ready = false;
+    for (int i = 0; i < kUNetLayers; ++i) {
+        const UNetLayerShape L = unet_layer(i);
+        const int cin = L.cin1 + L.cin2;
+        if (!layers[i].weights || !layers[i].bias || layers[i].cin != cin || layers[i].cout != L.cout) {
+            return fail(ctx, "rc_unet_set_weights: layer %d must be %d -> %d channels (got %d -> %d)", i, cin, L.cout,
+                        layers[i].cin, layers[i].cout);
+        }
+        // OIHW fp16 -> [cout][tap][cin] fp32 (exact)
+        std::vector<float> w(size_t(L.cout) * 9 * cin), b(L.cout);
+        for (int co = 0; co < L.cout; ++co) {
+            b[co] = half_bits_to_float(layers[i].bias[co]);
+            for (int ci = 0; ci < cin; ++ci) {
+                for (int t = 0; t < 9; ++t) {
+                    w[(size_t(co) * 9 + t) * cin + ci] = half_bits_to_float(layers[i].weights[(size_t(co) * cin + ci) * 9 + t]);
+                }
+            }
+        }
+        cudaFree(ctx->unet_w[i]);
+        cudaFree(ctx->unet_b[i]);
+        ctx->unet_w[i] = ctx->unet_b[i] = nullptr;
+        CU_CHECK(ctx, cudaMalloc(&ctx->unet_w[i], w.size() * sizeof(float)));
+        CU_CHECK(ctx, cudaMalloc(&ctx->unet_b[i], b.size() * sizeof(float)));
+        CU_CHECK(ctx, cudaMemcpy(ctx->unet_w[i], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU_CHECK(ctx, cudaMemcpy(ctx->unet_b[i], b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    ctx->unet_ready = true;
+    return 0;
+}
+
+int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags) {
+    if (!ctx || !rect) {
+        return fail(ctx, "rc_denoise_unet: null argument");
+    }
+    cudaSetDevice(ctx->device);
+    if (!ctx->unet_ready) {
+        return fail(ctx, "rc_denoise_unet: no weights (rc_unet_set_weights)");
+    }
+    if (pass < -1 || pass >= kUNetLayers) {
+        return fail(ctx, "rc_denoise_unet: pass %d out of range", pass);
+    }
+    const rc_rect &r = *rect;
+    if (r.x < 0 || r.y < 0 || r.w <= 0 || r.h <= 0 || r.x + r.w > ctx->w || r.y + r.h > ctx->h) {
+        return fail(ctx, "rc_denoise_unet: rect (%d,%d,%d,%d) is outside the %dx%d frame", r.x, r.y, r.w, r.h, ctx->w, ctx->h);
+    }
+    if (unet_alloc_tensors(ctx)) {
+        return 1;
+    }
+    (void)flags;
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0 = ctx->user_events[8], e1 = ctx->user_events[9];
+    if (e0 && e1) {
+        cudaEventRecord(e0, s);
+    }
+    const int wr = ctx->unet_tw, hr = ctx->unet_th;
+    // which tensors each pass reads: main input, skip input (-1 none, -2 the frame's feature planes)
+    static const int in1_of[16] = {-2, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14};
+    static const int in2_of[16] = {-1, -1, -1, -1, -1, -1, -1, 3, -1, 2, -1, 1, -1, -2, -1, -1};
+    for (int i = (pass < 0 ? 0 : pass); i <= (pass < 0 ? kUNetLayers - 1 : pass); ++i) {
+        const UNetLayerShape L = unet_layer(i);
+        UNetConvParams p{};
+        p.fb = ctx->fb;
+        p.cin1 = L.cin1;
+        p.cin2 = L.cin2;
+        p.cout = L.cout;
+        p.w = wr >> L.level;
+        p.h = hr >> L.level;
+        p.up = L.up ? 1 : 0;
+        p.pool = L.pool ? 1 : 0;
+        p.feat_in1 = in1_of[i] == -2;
+        p.feat_in2 = in2_of[i] == -2;
+        p.last = (i == kUNetLayers - 1);
+        p.inv_gamma = ctx->last_inv_gamma;
+        p.in1 = in1_of[i] >= 0 ? ctx->unet_t[in1_of[i]] : nullptr;
+        p.in2 = in2_of[i] >= 0 ? ctx->unet_t[in2_of[i]] : nullptr;
+        p.weights = ctx->unet_w[i];
+        p.bias = ctx->unet_b[i];
+        p.out = (i < 15) ? ctx->unet_t[i] : nullptr;
+        // the region on this level's grid: passes < 15 round the frame rect up to 16 first (RendererCPU.h:797-801)
+        int x0 = r.x, y0 = r.y, x1 = r.x + r.w, y1 = r.y + r.h;
+        if (i < 15) {
+            x1 = x0 + (r.w + 15) / 16 * 16;
+            y1 = y0 + (r.h + 15) / 16 * 16;
+        }
+        const int sh = L.level;
+        p.rx = x0 >> sh;
+        p.ry = y0 >> sh;
+        p.rw = min(((x1 + (1 << sh) - 1) >> sh), p.w) - p.rx;
+        p.rh = min(((y1 + (1 << sh) - 1) >> sh), p.h) - p.ry;
+        const dim3 grid((p.rw + kConvTile - 1) / kConvTile, (p.rh + kConvTile - 1) / kConvTile,
+                        (p.cout + kConvCoutBlk - 1) / kConvCoutBlk);
+        k_unet_conv_f32<<<grid, 64, 0, s>>>(p);
+    }
+    if (e0 && e1) {
+        cudaEventRecord(e1, s);
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    CU_CHECK(ctx, cudaGetLastError());
+    if (e0 && e1) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ctx->stats_us[8] += uint64_t(double(ms) * 1000.0);
     }
     return 0;
 }

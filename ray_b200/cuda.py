@@ -67,6 +67,8 @@ def load_library():
         "rc_event_record": (C.c_int, [vp, C.c_int]),
         "rc_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, P(C.c_float)]),
         "rc_readback_async": (C.c_int, [vp, C.c_int, P(capi.rc_rect), vp, C.c_int]),
+        "rc_unet_set_weights": (C.c_int, [vp, vp]),
+        "rc_denoise_unet": (C.c_int, [vp, C.c_int, P(capi.rc_rect), C.c_uint32]),
         "rc_comm_init": (C.c_int, [P(vp), C.c_int, P(vp)]),
         "rc_comm_destroy": (None, [vp]),
         "rc_comm_last_error": (C.c_char_p, [vp]),
@@ -95,7 +97,7 @@ EXPORTED_SYMBOLS = [
     "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
     "rc_event_record", "rc_event_elapsed_ms", "rc_readback_async", "rc_comm_init", "rc_comm_destroy", "rc_comm_last_error",
     "rc_comm_strip", "rc_comm_upload_scene", "rc_comm_upload_tables", "rc_comm_render", "rc_comm_sync", "rc_gather",
-    "rc_gather_device", "rc_comm_get_counters",
+    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet",
 ]
 
 
@@ -165,6 +167,23 @@ class Context:
 
     def render(self, p: capi.rc_pass_desc):
         self._check(self.lib.rc_render(self._ctx, C.byref(p)), "rc_render")
+
+    def unet_set_weights(self, layers):
+        """layers: 16 x (weights fp16 ndarray [cout, cin, 3, 3], bias fp16 ndarray [cout]) in pass order"""
+        class L(C.Structure):
+            _fields_ = [("weights", C.c_void_p), ("bias", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32)]
+        arr = (L * 16)()
+        keep = []
+        for i, (w, b) in enumerate(layers):
+            w = np.ascontiguousarray(w, dtype=np.float16)
+            b = np.ascontiguousarray(b, dtype=np.float16)
+            keep += [w, b]
+            arr[i] = L(w.ctypes.data, b.ctypes.data, w.shape[1], w.shape[0])
+        self._check(self.lib.rc_unet_set_weights(self._ctx, C.byref(arr)), "rc_unet_set_weights")
+
+    def denoise_unet(self, rect, flags=0, pass_index=-1):
+        r = capi.rc_rect(*rect)
+        self._check(self.lib.rc_denoise_unet(self._ctx, pass_index, C.byref(r), flags), "rc_denoise_unet")
 
     def denoise_nlm(self, rect, iteration):
         r = capi.rc_rect(*rect)

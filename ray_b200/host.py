@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libray_host.so")
 FINAL, RAW, BASE_COLOR, DEPTH_NORMALS = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
-    "rh_create_renderer", "rh_create_renderer_multi", "rh_device_count", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
+    "rh_create_renderer", "rh_create_renderer_multi", "rh_device_count", "rh_set_unet_weights", "rh_denoise_unet", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
     "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_denoise", "rh_add_texture", "rh_add_material_node",
     "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_add_light_directional",
     "rh_add_light_sphere", "rh_add_light_spot", "rh_add_light_rect", "rh_add_light_disk", "rh_add_light_line",
@@ -47,6 +47,8 @@ def load_library():
         "rh_create_renderer": (vp, [C.c_int, C.c_int, C.c_int]),
         "rh_create_renderer_multi": (vp, [C.c_int, C.c_int, C.c_char_p]),
         "rh_device_count": (C.c_int, [vp]),
+        "rh_set_unet_weights": (C.c_int, [vp, vp, C.c_uint32]),
+        "rh_denoise_unet": (C.c_int, [vp, P(capi.rc_rect), C.c_int]),
         "rh_destroy_renderer": (None, [vp]),
         "rh_device_name": (C.c_char_p, [vp]),
         "rh_error_count": (C.c_int, [vp]),
@@ -261,6 +263,26 @@ class Renderer:
         self.lib.rh_render(self.h, scene.h, C.byref(r), C.byref(it), count)
         self.check()
         return it.value
+
+    def set_unet_weights(self, layers, flags=0):
+        """layers: 16 x (weights fp16 [cout, cin, 3, 3], bias fp16 [cout]) in pass order (include/ray_cuda.h)"""
+        class L(C.Structure):
+            _fields_ = [("weights", C.c_void_p), ("bias", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32)]
+        arr = (L * 16)()
+        keep = []
+        for i, (w, b) in enumerate(layers):
+            w = np.ascontiguousarray(w, dtype=np.float16)
+            b = np.ascontiguousarray(b, dtype=np.float16)
+            keep += [w, b]
+            arr[i] = L(w.ctypes.data, b.ctypes.data, w.shape[1], w.shape[0])
+        if self.lib.rh_set_unet_weights(self.h, C.byref(arr), flags) != 0:
+            self.check()
+
+    def denoise_unet(self, rect, iteration):
+        r = capi.rc_rect(*rect)
+        n = self.lib.rh_denoise_unet(self.h, C.byref(r), int(iteration))
+        self.check()
+        return n
 
     def denoise(self, rect, iteration):
         """RendererBase::DenoiseImage(region): joint NLM filter; results through pixels(FINAL) / pixels(RAW)."""

@@ -11,6 +11,7 @@ import numpy as np
 from ray_b200 import capi
 from ray_b200.cuda import HIT_DTYPE, RAY_DTYPE, SHADOW_DTYPE
 
+P_u16 = C.POINTER(C.c_uint16)
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_ROOT, "oracle", "_ref", "libray_oracle.so")
 _lib = None
@@ -59,6 +60,8 @@ def load():
         "ro_renderer_clear": (None, [vp, P(C.c_float)]),
         "ro_render": (None, [vp, vp, P(capi.rc_rect), P(C.c_int)]),
         "ro_denoise": (None, [vp, P(capi.rc_rect), C.c_int]),
+        "ro_denoise_unet": (C.c_int, [vp, P(capi.rc_rect), C.c_int]),
+        "ro_unet_layer": (None, [C.c_int, P(P(C.c_uint16)), P(C.c_int), P(P(C.c_uint16)), P(C.c_int)]),
         "ro_get_pixels": (P(C.c_float), [vp, C.c_int, P(C.c_int)]),
         "ro_get_stats": (None, [vp, P(C.c_uint64)]),
         "ro_render_mt": (C.c_double, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -81,6 +84,21 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def unet_layers():
+    """The reference's UNet weight set as 16 x (weights fp16 [cout, cin, 3, 3], bias fp16 [cout]) in pass order."""
+    lib = load()
+    out = []
+    for i in range(16):
+        w, b = P_u16(), P_u16()
+        wn, bn = C.c_int(), C.c_int()
+        lib.ro_unet_layer(i, C.byref(w), C.byref(wn), C.byref(b), C.byref(bn))
+        bias = np.ctypeslib.as_array(b, shape=(bn.value,)).view(np.float16).copy()
+        wts = np.ctypeslib.as_array(w, shape=(wn.value,)).view(np.float16).copy()
+        cout = bn.value
+        out.append((wts.reshape(cout, wn.value // (9 * cout), 3, 3), bias))
+    return out
 
 
 def pmj_table():
@@ -346,6 +364,11 @@ class Renderer:
         it = C.c_int(iteration)
         self.lib.ro_render(self.h, scene.h, C.byref(r), C.byref(it))
         return it.value
+
+    def denoise_unet(self, rect, iteration):
+        """RendererBase::InitUNetFilter + DenoiseImage(pass, region) for all 16 passes (the UNet overload)."""
+        r = capi.rc_rect(*rect)
+        return self.lib.ro_denoise_unet(self.h, C.byref(r), int(iteration))
 
     def denoise(self, rect, iteration):
         """RendererBase::DenoiseImage(region) (NLM)."""

@@ -231,3 +231,36 @@ def test_nlm_denoise_matches_reference_renderer(oracle_mod):
         assert bits_equal(final[sl], ref_final[sl]), f"rect {rect}: tonemapped L-inf {np.abs(final[sl] - ref_final[sl]).max()}"
     ref.close()
     pair.close()
+
+
+def test_unet_denoise_matches_reference_renderer(oracle_mod):
+    """RendererBase::DenoiseImage(pass, region) (SURVEY 8(f)-3, UNet half): same 8 spp accumulated on both sides
+    (bit-identical), then the 16-pass UNet with the reference's own weight set handed over through rc_unet_set_weights.
+    The fp32 path sums the same products in another order than the reference's 4-lane partial sums (and uses FMA), so the
+    filtered linear image agrees to rounding noise, not bitwise: tolerance 2e-4 relative to (1 + |value|)."""
+    desc = scenes.cornell_box(112, 80)  # 112 = 7 x 16, 80 = 5 x 16; a second case below is not a multiple of 16
+    for (w, h) in ((112, 80), (100, 70)):
+        desc = scenes.cornell_box(w, h)
+        pair = Pair(oracle_mod, desc)
+        spp = 8
+        ref = oracle_mod.Renderer(capi.RT_REFERENCE, w, h)
+        it = 0
+        for _ in range(spp):
+            it = ref.render(pair.osc, (0, 0, w, h), it)
+        pair.ctx.clear((0, 0, 0, 0))
+        for i in range(1, spp + 1):
+            pair.ctx.render(pair.make_pass(i))
+        assert bits_equal(pair.ctx.readback(capi.RC_BUF_RAW), ref.pixels(1))
+        ref.denoise_unet((0, 0, w, h), it)
+        pair.ctx.unet_set_weights(oracle_mod.unet_layers())
+        pair.ctx.denoise_unet((0, 0, w, h), flags=capi.RC_UNET_FP32)
+        ref_raw, ref_final = ref.pixels(1), ref.pixels(0)
+        raw, final = pair.ctx.readback(capi.RC_BUF_RAW), pair.ctx.readback(capi.RC_BUF_FINAL)
+        assert np.isfinite(raw).all()
+        err = np.abs(raw[..., :3] - ref_raw[..., :3]) / (1.0 + np.abs(ref_raw[..., :3]))
+        assert err.max() <= 2e-4, f"{w}x{h}: UNet (fp32) filtered image differs: max rel {err.max():g}"
+        assert np.abs(final[..., :3] - ref_final[..., :3]).max() <= 1e-3
+        # the filter actually filtered: the output is not the noisy input
+        assert np.abs(raw[..., :3] - pair.ctx.readback(capi.RC_BUF_FULL)[..., :3]).mean() > 1e-4
+        ref.close()
+        pair.close()
