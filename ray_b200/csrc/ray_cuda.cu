@@ -22,6 +22,7 @@
 #include "rt_sort.cuh"
 #include "rt_denoise.cuh"
 #include "rt_unet.cuh"
+#include "rt_unet_tc.cuh"
 
 using namespace rt;
 
@@ -73,6 +74,12 @@ struct rc_ctx {
     float *unet_t[15] = {};
     int unet_tw = 0, unet_th = 0; // rounded frame the tensors were sized for
     bool unet_ready = false;
+    // tensor-core path (rt_unet_tc.cuh): fp16 weights [9][n][in_cs], fp32 biases [n], bordered fp16 tensors
+    __half *unet_hw[kUNetLayers] = {};
+    float *unet_hb[kUNetLayers] = {};
+    __half *unet_ht[15] = {}, *unet_hx0 = nullptr, *unet_hs = nullptr, *unet_hg = nullptr;
+    int unet_htw = 0, unet_hth = 0;
+    void *tensor_map_encode = nullptr; // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint
     float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
     size_t nlm_scratch_elems = 0;
     float last_inv_gamma = 1.0f, last_variance_threshold = 0.0f; // tonemap_params_ / variance_threshold_ of the reference
@@ -854,6 +861,16 @@ void rc_destroy(rc_ctx *ctx) {
     for (float *t : ctx->unet_t) {
         cudaFree(t);
     }
+    for (int i = 0; i < kUNetLayers; ++i) {
+        cudaFree(ctx->unet_hw[i]);
+        cudaFree(ctx->unet_hb[i]);
+    }
+    for (__half *t : ctx->unet_ht) {
+        cudaFree(t);
+    }
+    cudaFree(ctx->unet_hx0);
+    cudaFree(ctx->unet_hs);
+    cudaFree(ctx->unet_hg);
     for (DevArray *a : {&ctx->dnodes, &ctx->blas_roots, &ctx->dmtris, &ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
                         &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {
@@ -1238,6 +1255,167 @@ int unet_alloc_tensors(rc_ctx *ctx) {
 }
 } // namespace
 
+// ---- tensor-core path of the UNet (rt_unet_tc.cuh) -------------------------------------------------------------------
+namespace {
+int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
+
+// real (16-padded) input channels of layer i on the tensor-core path and the position of original input channel ci
+int unet_tc_cin(int i) {
+    const UNetLayerShape L = unet_layer(i);
+    return round_up_i(L.cin1, 16) + (L.cin2 ? round_up_i(L.cin2, 16) : 0);
+}
+int unet_tc_cin_pos(int i, int ci) {
+    const UNetLayerShape L = unet_layer(i);
+    return ci < L.cin1 ? ci : round_up_i(L.cin1, 16) + (ci - L.cin1);
+}
+
+size_t unet_h_elems(int w, int h, int cs) { return size_t(w + 2) * size_t(h + 2) * size_t(cs); }
+
+int unet_tc_alloc(rc_ctx *ctx) {
+    const int wr = (ctx->w + 15) / 16 * 16, hr = (ctx->h + 15) / 16 * 16;
+    if (ctx->unet_htw == wr && ctx->unet_hth == hr && ctx->unet_hx0) {
+        return 0;
+    }
+    for (__half *&t : ctx->unet_ht) {
+        cudaFree(t);
+        t = nullptr;
+    }
+    cudaFree(ctx->unet_hx0);
+    cudaFree(ctx->unet_hs);
+    cudaFree(ctx->unet_hg);
+    ctx->unet_hx0 = ctx->unet_hs = ctx->unet_hg = nullptr;
+    ctx->unet_htw = ctx->unet_hth = 0;
+    auto alloc0 = [&](__half **p, size_t n) -> int {
+        CU_CHECK(ctx, cudaMalloc(p, n * sizeof(__half)));
+        CU_CHECK(ctx, cudaMemsetAsync(*p, 0, n * sizeof(__half), ctx->stream)); // borders and padded channels stay zero for good
+        return 0;
+    };
+    for (int i = 0; i < 15; ++i) {
+        int c, sh;
+        unet_tensor_shape(i, c, sh);
+        if (alloc0(&ctx->unet_ht[i], unet_h_elems(wr >> sh, hr >> sh, round_up_i(c, 64)))) {
+            return 1;
+        }
+    }
+    // network input (64), conv output before pooling (<= 128 stride at level 0..3: sized for level 0 with 128), decoder input
+    if (alloc0(&ctx->unet_hx0, unet_h_elems(wr, hr, 64)) || alloc0(&ctx->unet_hs, unet_h_elems(wr, hr, 128)) ||
+        alloc0(&ctx->unet_hg, unet_h_elems(wr, hr, 192))) {
+        return 1;
+    }
+    ctx->unet_htw = wr;
+    ctx->unet_hth = hr;
+    return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp16 tensor map: `rows` rows of `cs` channels, box = [box_rows][64 channels], 128-byte swizzle
+int make_map(rc_ctx *ctx, CUtensorMap *m, const void *base, int cs, size_t rows, int box_rows) {
+    if (!ctx->tensor_map_encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            return fail(ctx, "rc_denoise_unet: cuTensorMapEncodeTiled is not available from the driver");
+        }
+        ctx->tensor_map_encode = fn;
+    }
+    const cuuint64_t dims[2] = {cuuint64_t(cs), cuuint64_t(rows)};
+    const cuuint64_t strides[1] = {cuuint64_t(cs) * 2};
+    const cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->tensor_map_encode)(
+        m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        return fail(ctx, "rc_denoise_unet: cuTensorMapEncodeTiled failed (%d)", int(r));
+    }
+    return 0;
+}
+
+// one convolution on the tensor cores: `in` (bordered, cin real channels, stride in_cs) -> out
+int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in, int in_cs, int cin, int w, int h, __half *out, int out_cs,
+                 const rc_rect &r) {
+    const UNetLayerShape L = unet_layer(layer);
+    const int n = round_up_i(L.cout, 16);
+    CUtensorMap map_a, map_b;
+    if (make_map(ctx, &map_a, in, in_cs, size_t(w + 2) * size_t(h + 2), tc::kTileM) ||
+        make_map(ctx, &map_b, ctx->unet_hw[layer], in_cs, size_t(9) * n, n)) {
+        return 1;
+    }
+    tc::ConvTcParams p{};
+    p.bias = ctx->unet_hb[layer];
+    p.out = out;
+    p.fb = ctx->fb;
+    p.w = w;
+    p.h = h;
+    p.cin = cin;
+    p.in_cs = in_cs;
+    p.n = n;
+    p.cout = L.cout;
+    p.out_cs = out_cs;
+    p.tmem_cols = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
+    p.last = (layer == kUNetLayers - 1);
+    p.rx = r.x, p.ry = r.y, p.rw = r.w, p.rh = r.h;
+    p.inv_gamma = ctx->last_inv_gamma;
+    const int stage_bytes = tc::kATileBytes + ((n * tc::kBlockK * 2 + 1023) & ~1023);
+    const int smem = tc::kStages * stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::k_unet_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    tc::k_unet_conv_tc<<<dim3((w + tc::kTileM - 1) / tc::kTileM, h), tc::kThreads, smem, ctx->stream>>>(map_a, map_b, p);
+    return 0;
+}
+
+int unet_run_tc(rc_ctx *ctx, int pass, const rc_rect &r) {
+    if (unet_tc_alloc(ctx)) {
+        return 1;
+    }
+    cudaStream_t s = ctx->stream;
+    const int wr = ctx->unet_htw, hr = ctx->unet_hth;
+    static const int skip_of[16] = {-1, -1, -1, -1, -1, -1, -1, 3, -1, 2, -1, 1, -1, -2, -1, -1};
+    for (int i = (pass < 0 ? 0 : pass); i <= (pass < 0 ? kUNetLayers - 1 : pass); ++i) {
+        const UNetLayerShape L = unet_layer(i);
+        const int w = wr >> L.level, h = hr >> L.level;
+        const __half *in;
+        int in_cs, cin = unet_tc_cin(i);
+        if (i == 0) {
+            tc::k_unet_feat_h<<<dim3((wr + 127) / 128, hr), 128, 0, s>>>(ctx->fb, ctx->unet_hx0, wr, hr, 64);
+            in = ctx->unet_hx0;
+            in_cs = 64;
+        } else if (L.up) {
+            // decoder: up-sample the previous tensor and append the skip tensor (or the network input)
+            const int ca = L.cin1, a_cs = round_up_i(ca, 64);
+            const __half *b = skip_of[i] == -2 ? ctx->unet_hx0 : ctx->unet_ht[skip_of[i]];
+            const int cb = skip_of[i] == -2 ? 16 : L.cin2, b_cs = skip_of[i] == -2 ? 64 : round_up_i(L.cin2, 64);
+            in_cs = round_up_i(cin, 64);
+            tc::k_unet_gather_h<<<dim3(w, h), 64, 0, s>>>(ctx->unet_ht[i - 1], a_cs, ca, b, b_cs, cb, ctx->unet_hg, in_cs, w, h);
+            in = ctx->unet_hg;
+        } else {
+            in = ctx->unet_ht[i - 1];
+            in_cs = round_up_i(L.cin1, 64);
+        }
+        const int out_cs = round_up_i(L.cout, 64);
+        if (i == kUNetLayers - 1) {
+            if (unet_conv_tc(ctx, i, in, in_cs, cin, w, h, nullptr, 0, r)) {
+                return 1;
+            }
+        } else if (L.pool) {
+            if (unet_conv_tc(ctx, i, in, in_cs, cin, w, h, ctx->unet_hs, out_cs, r)) {
+                return 1;
+            }
+            tc::k_unet_pool_h<<<dim3(w >> 1, h >> 1), 64, 0, s>>>(ctx->unet_hs, out_cs, ctx->unet_ht[i], out_cs, L.cout, w, h);
+        } else if (unet_conv_tc(ctx, i, in, in_cs, cin, w, h, ctx->unet_ht[i], out_cs, r)) {
+            return 1;
+        }
+    }
+    return 0;
+}
+} // namespace
+
 int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]) {
     if (!ctx || !layers) {
         return fail(ctx, "rc_unet_set_weights: null argument");
@@ -1268,6 +1446,26 @@ int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]) {
         CU_CHECK(ctx, cudaMalloc(&ctx->unet_b[i], b.size() * sizeof(float)));
         CU_CHECK(ctx, cudaMemcpy(ctx->unet_w[i], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU_CHECK(ctx, cudaMemcpy(ctx->unet_b[i], b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // tensor-core path: the fp16 bits as they came, [tap][cout padded to 16][input channel stride], zero padded
+        const int n = round_up_i(L.cout, 16), in_cs = round_up_i(unet_tc_cin(i), 64);
+        std::vector<uint16_t> hw(size_t(9) * n * in_cs, 0);
+        std::vector<float> hb(n, 0.0f);
+        for (int co = 0; co < L.cout; ++co) {
+            hb[co] = b[co];
+            for (int ci = 0; ci < cin; ++ci) {
+                for (int t = 0; t < 9; ++t) {
+                    hw[(size_t(t) * n + co) * in_cs + unet_tc_cin_pos(i, ci)] = layers[i].weights[(size_t(co) * cin + ci) * 9 + t];
+                }
+            }
+        }
+        cudaFree(ctx->unet_hw[i]);
+        cudaFree(ctx->unet_hb[i]);
+        ctx->unet_hw[i] = nullptr;
+        ctx->unet_hb[i] = nullptr;
+        CU_CHECK(ctx, cudaMalloc(&ctx->unet_hw[i], hw.size() * 2));
+        CU_CHECK(ctx, cudaMalloc(&ctx->unet_hb[i], hb.size() * sizeof(float)));
+        CU_CHECK(ctx, cudaMemcpy(ctx->unet_hw[i], hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+        CU_CHECK(ctx, cudaMemcpy(ctx->unet_hb[i], hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     ctx->unet_ready = true;
     return 0;
@@ -1288,14 +1486,29 @@ int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags) 
     if (r.x < 0 || r.y < 0 || r.w <= 0 || r.h <= 0 || r.x + r.w > ctx->w || r.y + r.h > ctx->h) {
         return fail(ctx, "rc_denoise_unet: rect (%d,%d,%d,%d) is outside the %dx%d frame", r.x, r.y, r.w, r.h, ctx->w, ctx->h);
     }
-    if (unet_alloc_tensors(ctx)) {
-        return 1;
-    }
-    (void)flags;
     cudaStream_t s = ctx->stream;
     cudaEvent_t e0 = ctx->user_events[8], e1 = ctx->user_events[9];
     if (e0 && e1) {
         cudaEventRecord(e0, s);
+    }
+    if ((flags & RC_UNET_FP32) == 0) {
+        if (unet_run_tc(ctx, pass, r)) {
+            return 1;
+        }
+        if (e0 && e1) {
+            cudaEventRecord(e1, s);
+        }
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        CU_CHECK(ctx, cudaGetLastError());
+        if (e0 && e1) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ctx->stats_us[8] += uint64_t(double(ms) * 1000.0);
+        }
+        return 0;
+    }
+    if (unet_alloc_tensors(ctx)) {
+        return 1;
     }
     const int wr = ctx->unet_tw, hr = ctx->unet_th;
     // which tensors each pass reads: main input, skip input (-1 none, -2 the frame's feature planes)

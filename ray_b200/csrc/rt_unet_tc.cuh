@@ -1,0 +1,280 @@
+// rt_unet_tc.cuh -- the UNet's 3x3 convolutions as implicit GEMMs on the 5th-generation tensor cores (sm_100a):
+// tcgen05.mma with the accumulator in TMEM, operands staged by TMA (cp.async.bulk.tensor) into 128-byte-swizzled shared
+// memory, an mbarrier pipeline between one TMA-producer thread, one MMA-issuer thread and four epilogue warps.
+// This is the one dense contraction on the path; the reference's counterpart is the
+// cooperative-matrix shader internal/shaders/convolution.comp.glsl.  fp16 operands (the network's weights ARE fp16;
+// activations are rounded to fp16 between layers like the reference's GPU path), fp32 accumulation.
+//
+// Data layout (device only): every activation tensor is NHWC fp16 with a one-pixel zero border and a channel stride
+// padded to a multiple of 64: element (y, x, c) of an H x W grid sits at ((y + 1) (W + 2) + (x + 1)) Cs + c.  Padded
+// channels and the border are zero and are never written, so a convolution tap is a plain window of this array: the
+// A operand of tap (dy, dx) for the 128 output pixels (y, x0 .. x0 + 127) is the 2-D box [128 pixels][64 channels]
+// starting at pixel (y + dy) (W + 2) + x0 + dx -- one TMA load, no im2col, zero padding for free.  Weights are stored
+// [tap][cout padded to 16][Cs] fp16: the B operand of (tap, 64-channel block) is the box [cout][64].
+//
+// GEMM per CTA: D[128 pixels][N = cout] += sum over 9 taps x (Cs / 64) blocks of A[128][64] B[N][64]^T, K = 16 per
+// tcgen05.mma, M = 128, D in N TMEM columns (fp32).  Epilogue: tcgen05.ld -> bias + ReLU -> fp16 -> NHWC store (or, for
+// the last layer, inverse HDR transfer + display transform into the RAW / FINAL planes).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "rt_unet.cuh"
+
+namespace rt {
+namespace tc {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;              // output pixels per CTA (one row segment)
+constexpr int kBlockK = 64;              // channels per pipeline stage (one 128-byte swizzle row)
+constexpr int kThreads = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kATileBytes = kTileM * kBlockK * 2;
+
+RT_DEV uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+RT_DEV void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+RT_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RT_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+RT_DEV void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+RT_DEV void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+RT_DEV void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+RT_DEV void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+RT_DEV void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+                 "}" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// K-major operand tile, rows of 128 bytes, 128-byte swizzle, 8-row groups 1024 bytes apart (cute/arch/mma_sm100_desc.hpp)
+RT_DEV uint64_t umma_desc_sw128(const void *smem_tile) {
+    const uint64_t addr = uint64_t(smem_u32(smem_tile));
+    return ((addr >> 4) & 0x3fffull) | (1ull << 16) /* LBO (ignored for swizzled K-major) */ |
+           (uint64_t(1024 >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version of sm_100 */ | (2ull << 61) /* SWIZZLE_128B */;
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = fp16, both K-major, M = 128, N
+RT_DEV uint32_t umma_idesc_f16(int n) { return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileM >> 4) << 24); }
+
+struct ConvTcParams {
+    const float *bias;   // [n_pad] fp32 (zero for padded channels)
+    __half *out;         // bordered NHWC fp16, channel stride out_cs; null for the last layer
+    FrameBufs fb;        // last layer: RAW / FINAL planes
+    int w, h;            // convolution grid
+    int cin;             // real input channels (multiple of 16)
+    int in_cs;           // input channel stride (multiple of 64)
+    int n;               // output channels padded to 16 (= UMMA N)
+    int cout;            // real output channels
+    int out_cs;
+    int tmem_cols;       // power of two >= max(32, n)
+    int last;
+    int rx, ry, rw, rh;  // last layer: frame rect whose pixels are written
+    float inv_gamma;
+};
+
+// dynamic shared memory: kStages x (A tile 16 KB + B tile n x 128 B), 1024-byte aligned
+__global__ void __launch_bounds__(kThreads) k_unet_conv_tc(const __grid_constant__ CUtensorMap map_a,
+                                                           const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the 128-byte swizzle pattern repeats every 1024 bytes of SHARED address: align the stage buffers in that space
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ uint32_t s_tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_tile_bytes = p.n * kBlockK * 2;
+    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) & ~1023);
+    const int x0 = blockIdx.x * kTileM, y = blockIdx.y;
+    const int nkb = (p.cin + kBlockK - 1) / kBlockK;
+    const int steps = 9 * nkb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"(uint32_t(p.tmem_cols)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----
+            for (int s = 0; s < steps; ++s) {
+                const int stage = s % kStages;
+                if (s >= kStages) {
+                    mbar_wait(&empty_bar[stage], ((s / kStages) - 1) & 1);
+                }
+                const int tap = s / nkb, kb = s % nkb;
+                const int dy = tap / 3, dx = tap % 3;
+                uint8_t *a = smem + size_t(stage) * stage_bytes, *b = a + kATileBytes;
+                mbar_expect_tx(&full_bar[stage], uint32_t(kATileBytes + b_tile_bytes));
+                tma_load_2d(a, &map_a, &full_bar[stage], kb * kBlockK, (y + dy) * (p.w + 2) + x0 + dx);
+                tma_load_2d(b, &map_b, &full_bar[stage], kb * kBlockK, tap * p.n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            const uint32_t idesc = umma_idesc_f16(p.n);
+            for (int s = 0; s < steps; ++s) {
+                const int stage = s % kStages;
+                mbar_wait(&full_bar[stage], (s / kStages) & 1);
+                tcgen05_fence_after();
+                const int kb = s % nkb;
+                const int kcount = min(kBlockK, p.cin - kb * kBlockK) / 16;
+                const uint8_t *a = smem + size_t(stage) * stage_bytes, *b = a + kATileBytes;
+                const uint64_t adesc = umma_desc_sw128(a), bdesc = umma_desc_sw128(b);
+                for (int k = 0; k < kcount; ++k) {
+                    // 16 fp16 = 32 bytes further along the swizzled 128-byte row: start-address field += 2
+                    umma_f16(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (s > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]); // frees the stage once these MMAs have read it
+            }
+            umma_commit(&accum_bar); // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warps 2..5; a warp may only touch the TMEM lanes [32 (warp % 4), +32) ----
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane; // GEMM row = pixel x0 + row
+        const int x = x0 + row;
+        mbar_wait(&accum_bar, 0);
+        tcgen05_fence_after();
+        float outv[3] = {0.0f, 0.0f, 0.0f};
+        for (int c0 = 0; c0 < p.n; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + (uint32_t(lane_base) << 16) + uint32_t(c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+                         "[%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (p.last) {
+                if (c0 == 0) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        outv[i] = fmaxf(0.0f, __uint_as_float(r[i]) + p.bias[i]);
+                    }
+                }
+                continue;
+            }
+            if (x < p.w) {
+                __half2 h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float v0 = fmaxf(0.0f, __uint_as_float(r[2 * i]) + p.bias[c0 + 2 * i]);
+                    const float v1 = fmaxf(0.0f, __uint_as_float(r[2 * i + 1]) + p.bias[c0 + 2 * i + 1]);
+                    h[i] = __floats2half2_rn(v0, v1);
+                }
+                // padded output channels (>= cout) have zero weights and zero bias: they are written as ReLU(0) = 0
+                uint4 *dst = reinterpret_cast<uint4 *>(p.out + (size_t(y + 1) * (p.w + 2) + size_t(x + 1)) * p.out_cs + c0);
+                dst[0] = *reinterpret_cast<const uint4 *>(&h[0]);
+                dst[1] = *reinterpret_cast<const uint4 *>(&h[4]);
+            }
+        }
+        if (p.last && x >= p.rx && x < p.rx + p.rw && y >= p.ry && y < p.ry + p.rh) {
+            const int pix = y * p.fb.w + x;
+            const float4 full = p.fb.full[pix];
+            float4 c = make_float4(unet_tf::output_hdr(outv[0]), unet_tf::output_hdr(outv[1]), unet_tf::output_hdr(outv[2]), full.w);
+            p.fb.raw[pix] = c;
+            c.x = tonemap_standard(c.x);
+            c.y = tonemap_standard(c.y);
+            c.z = tonemap_standard(c.z);
+            if (p.inv_gamma != 1.0f) {
+                c.x = libm_powf(c.x, p.inv_gamma);
+                c.y = libm_powf(c.y, p.inv_gamma);
+                c.z = libm_powf(c.z, p.inv_gamma);
+            }
+            c.x = sse_max(0.0f, sse_min(c.x, 1.0f));
+            c.y = sse_max(0.0f, sse_min(c.y, 1.0f));
+            c.z = sse_max(0.0f, sse_min(c.z, 1.0f));
+            c.w = sse_max(0.0f, sse_min(c.w, 1.0f));
+            p.fb.final[pix] = c;
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols)));
+    }
+}
+
+// ---- the element-wise helpers around the convolutions (fp16 bordered tensors) -----------------------------------------
+// network input: 9 features in a 64-channel-stride tensor (channels 9..63 stay zero)
+__global__ void k_unet_feat_h(FrameBufs fb, __half *out, int w, int h, int cs) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) {
+        return;
+    }
+    float f[kUNetInCh];
+    unet_features(fb, x, y, f);
+    __half *dst = out + (size_t(y + 1) * (w + 2) + size_t(x + 1)) * cs;
+#pragma unroll
+    for (int i = 0; i < kUNetInCh; ++i) {
+        dst[i] = __float2half_rn(f[i]);
+    }
+}
+
+// decoder input: nearest 2x up-sampling of `a` (ca channels, half resolution) ++ skip tensor `b` (cb channels)
+__global__ void k_unet_gather_h(const __half *__restrict__ a, int a_cs, int ca, const __half *__restrict__ b, int b_cs, int cb,
+                                __half *__restrict__ out, int out_cs, int w, int h) {
+    const int x = blockIdx.x, y = blockIdx.y;
+    const int wa = w >> 1;
+    const __half *pa = a + (size_t((y >> 1) + 1) * (wa + 2) + size_t((x >> 1) + 1)) * a_cs;
+    const __half *pb = b + (size_t(y + 1) * (w + 2) + size_t(x + 1)) * b_cs;
+    __half *po = out + (size_t(y + 1) * (w + 2) + size_t(x + 1)) * out_cs;
+    for (int c = threadIdx.x; c < ca + cb; c += blockDim.x) {
+        po[c] = (c < ca) ? pa[c] : pb[c - ca];
+    }
+}
+
+// 2 x 2 max pooling of a full-resolution tensor into the half-resolution one
+__global__ void k_unet_pool_h(const __half *__restrict__ in, int in_cs, __half *__restrict__ out, int out_cs, int c, int w, int h) {
+    const int x = blockIdx.x, y = blockIdx.y; // output grid (w/2 x h/2)
+    const int wo = w >> 1;
+    const __half *p0 = in + (size_t(2 * y + 1) * (w + 2) + size_t(2 * x + 1)) * in_cs;
+    const __half *p1 = p0 + size_t(w + 2) * in_cs;
+    __half *po = out + (size_t(y + 1) * (wo + 2) + size_t(x + 1)) * out_cs;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const float m = fmaxf(fmaxf(__half2float(p0[i]), __half2float(p0[in_cs + i])),
+                              fmaxf(__half2float(p1[i]), __half2float(p1[in_cs + i])));
+        po[i] = __float2half_rn(m);
+    }
+}
+
+} // namespace tc
+} // namespace rt

@@ -264,3 +264,37 @@ def test_unet_denoise_matches_reference_renderer(oracle_mod):
         assert np.abs(raw[..., :3] - pair.ctx.readback(capi.RC_BUF_FULL)[..., :3]).mean() > 1e-4
         ref.close()
         pair.close()
+
+
+def test_unet_tensor_core_path_matches_reference_renderer(oracle_mod):
+    """The same UNet through the tcgen05 path (fp16 operands, fp32 accumulation in TMEM, rt_unet_tc.cuh) against the
+    reference's fp32 CPU filter.  Activations are rounded to fp16 between the 16 layers (as on the reference's own GPU
+    path), so the bar is fp16-level agreement: max relative error 3e-2 of (1 + |value|), mean 2e-3, and > 40 dB PSNR
+    against the fp32 device path on the tonemapped image."""
+    for (w, h) in ((160, 96), (100, 70)):
+        desc = scenes.cornell_box(w, h)
+        pair = Pair(oracle_mod, desc)
+        spp = 8
+        ref = oracle_mod.Renderer(capi.RT_REFERENCE, w, h)
+        it = 0
+        for _ in range(spp):
+            it = ref.render(pair.osc, (0, 0, w, h), it)
+        pair.ctx.clear((0, 0, 0, 0))
+        for i in range(1, spp + 1):
+            pair.ctx.render(pair.make_pass(i))
+        ref.denoise_unet((0, 0, w, h), it)
+        ref_raw = ref.pixels(1)
+        pair.ctx.unet_set_weights(oracle_mod.unet_layers())
+        pair.ctx.denoise_unet((0, 0, w, h), flags=capi.RC_UNET_FP32)
+        f32_final = pair.ctx.readback(capi.RC_BUF_FINAL)
+        pair.ctx.denoise_unet((0, 0, w, h), flags=capi.RC_UNET_TENSOR_CORES)
+        raw, final = pair.ctx.readback(capi.RC_BUF_RAW), pair.ctx.readback(capi.RC_BUF_FINAL)
+        assert np.isfinite(raw).all()
+        err = np.abs(raw[..., :3] - ref_raw[..., :3]) / (1.0 + np.abs(ref_raw[..., :3]))
+        mse = float(((final[..., :3] - f32_final[..., :3]) ** 2).mean())
+        psnr = 10.0 * np.log10(1.0 / max(mse, 1e-12))
+        print(f"unet tc {w}x{h}: max rel {err.max():.3g} mean rel {err.mean():.3g} PSNR vs fp32 path {psnr:.1f} dB")
+        assert err.max() <= 3e-2 and err.mean() <= 2e-3, f"{w}x{h}: max rel {err.max():g}, mean rel {err.mean():g}"
+        assert psnr > 40.0
+        ref.close()
+        pair.close()
