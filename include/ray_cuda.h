@@ -178,6 +178,17 @@ enum { RC_UNET_TENSOR_CORES = 0, RC_UNET_FP32 = 1 };
 int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]);
 int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags);
 
+/* Device build of a binary BVH over n primitive boxes (the fast builder of SURVEY.md section 8(f) row 4; reference:
+ * PreprocessPrims_HLBVH, internal/Core.cpp:574-720): Morton order of the box centroids, Karras' parallel radix tree,
+ * bottom-up box fit.  boxes: n x {min xyz, max xyz}.  nodes_out: 2n - 1 records {min[3], max[3], left, right, first,
+ * count}: internal nodes 0 .. n-2 (root 0, count 0, children = node indices), leaves n-1 .. 2n-2 (count 1, first = rank
+ * in Morton order).  order_out[rank] = index of the primitive.  n >= 2.  Blocking; all buffers are the caller's (host). */
+typedef struct rc_lbvh_node {
+    float mn[3], mx[3];
+    uint32_t left, right, first, count;
+} rc_lbvh_node;
+int rc_build_lbvh(rc_ctx *ctx, const float *boxes, uint32_t n, rc_lbvh_node *nodes_out, uint32_t *order_out);
+
 /* dst: rect.w*rect.h RGBA float pixels written with the given pitch (in pixels). */
 int rc_readback(rc_ctx *ctx, int which, const rc_rect *rect, float *dst, int pitch);
 int rc_readback_required_samples(rc_ctx *ctx, uint16_t *dst);

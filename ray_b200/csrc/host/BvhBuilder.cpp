@@ -1,6 +1,8 @@
 // BvhBuilder.cpp -- binned SAH build (see BvhBuilder.h for the role this plays).
 #include "BvhBuilder.h"
 
+#include "ray_cuda.h"
+
 #include <cmath>
 #include <numeric>
 
@@ -142,6 +144,44 @@ void BuildBinaryBVH(const std::vector<Aabb> &prims, const int max_leaf, std::vec
         stack.push_back({l + 1, mid, t.first + t.count - mid});
         stack.push_back({l, t.first, mid - t.first});
     }
+}
+
+bool BuildBinaryLBVH(rc_ctx *ctx, const std::vector<Aabb> &prims, std::vector<BinaryNode> &nodes,
+                     std::vector<uint32_t> &indices) {
+    static_assert(sizeof(BinaryNode) == sizeof(rc_lbvh_node) && sizeof(Aabb) == 6 * sizeof(float), "layout");
+    const uint32_t n = uint32_t(prims.size());
+    std::vector<rc_lbvh_node> raw(size_t(2) * n - 1);
+    indices.resize(n);
+    if (rc_build_lbvh(ctx, &prims[0].mn[0], n, raw.data(), indices.data()) != 0) {
+        return false;
+    }
+    // breadth-first renumbering from the root: parents before children
+    nodes.clear();
+    nodes.resize(raw.size());
+    std::vector<uint32_t> queue(raw.size());
+    uint32_t head = 0, tail = 0;
+    queue[tail++] = 0;
+    while (head < tail) {
+        const uint32_t dst = head;
+        const rc_lbvh_node &src = raw[queue[head++]];
+        BinaryNode &nd = nodes[dst];
+        for (int a = 0; a < 3; ++a) {
+            nd.box.mn[a] = src.mn[a];
+            nd.box.mx[a] = src.mx[a];
+        }
+        nd.first = src.first;
+        nd.count = src.count;
+        if (src.count == 0) {
+            if (tail + 2 > queue.size()) {
+                return false; // not a tree
+            }
+            nd.left = tail;
+            queue[tail++] = src.left;
+            nd.right = tail;
+            queue[tail++] = src.right;
+        }
+    }
+    return tail == uint32_t(raw.size());
 }
 
 } // namespace RayB200

@@ -12,6 +12,8 @@
 
 #include "../rt_types.h"
 
+struct rc_ctx;
+
 namespace RayB200 {
 
 struct Aabb {
@@ -48,6 +50,12 @@ struct BinaryNode {
 // permutation of [0, prims.size()).  Returns the root index (always 0) -- `nodes` is cleared first.
 void BuildBinaryBVH(const std::vector<Aabb> &prims, int max_leaf, std::vector<BinaryNode> &nodes,
                     std::vector<uint32_t> &indices);
+
+// Fast build: the binary tree comes from the device (rc_build_lbvh: Morton order + Karras radix tree + bottom-up fit,
+// ../rt_lbvh.cuh); this wrapper renumbers it breadth-first so that children follow their parent, the order the collapse
+// functions below walk.  Leaves hold one primitive each.  Returns false when the device call failed.
+bool BuildBinaryLBVH(rc_ctx *ctx, const std::vector<Aabb> &prims, std::vector<BinaryNode> &nodes,
+                     std::vector<uint32_t> &indices);
 
 // Collapse a binary BVH into 8-wide nodes (rt::WNode = wbvh_node_t).  Each binary leaf becomes a leaf WNode whose
 // child[0] = LEAF | leaf_payload(leaf) and child[1] = count.  Node ids are relative to out.size() at entry + `base`.

@@ -203,7 +203,7 @@ void Renderer::Clear(const color_rgba_t &c) {
     }
 }
 
-SceneBase *Renderer::CreateScene() { return new Scene(log_); }
+SceneBase *Renderer::CreateScene() { return new Scene(log_, ctx_); }
 
 void Renderer::SetSamplerTable(const uint32_t *table) {
     sampler_table_.assign(table, table + size_t(rt::kRandDims) * rt::kRandSamples * 2);

@@ -198,8 +198,9 @@ void InverseMatrix4(const float m[16], float out[16]) {
     }
 }
 
-Scene::Scene(ILog *log) {
+Scene::Scene(ILog *log, rc_ctx *build_ctx) {
     log_ = log;
+    build_ctx_ = build_ctx;
     SetEnvironment(environment_desc_t{{0, 0, 0}, {0, 0, 0}, 1, RS_INVALID, RS_INVALID, 0.0f, 0.0f});
 }
 Scene::~Scene() {
@@ -639,7 +640,18 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
     static const bool greedy = getenv("RAY_HOST_BVH") && !strcmp(getenv("RAY_HOST_BVH"), "greedy");
     std::vector<BinaryNode> bnodes;
     std::vector<uint32_t> order;
-    BuildBinaryBVH(boxes, greedy ? 8 : 1, bnodes, order);
+    bool built = false;
+    if (m.use_fast_bvh_build && !greedy && build_ctx_ && boxes.size() >= 2) {
+        // fast build (reference: PreprocessPrims_HLBVH, Core.cpp:574-720): Morton-order radix tree built on the device
+        built = BuildBinaryLBVH(build_ctx_, boxes, bnodes, order);
+        if (!built) {
+            log_->Error("Ray(CUDA): AddMesh: device BVH build failed: %s", rc_last_error(build_ctx_));
+            return MeshHandle{};
+        }
+    }
+    if (!built) {
+        BuildBinaryBVH(boxes, greedy ? 8 : 1, bnodes, order);
+    }
 
     // every leaf owns one 8-triangle block; lanes past the leaf's count repeat its last triangle (Core.cpp:533-535)
     std::vector<rt::WNode> wide;

@@ -87,6 +87,8 @@ class Scene final : public SceneBase {
     static uint64_t NextRevision();
     mutable uint64_t revision_ = NextRevision(); // renewed by Finalize: tells the renderer to re-upload
 
+    rc_ctx *build_ctx_ = nullptr;
+
     void RebuildTLAS_nolock();
     void RebuildLightTree_nolock();
     MaterialHandle AddMaterial_nolock(const shading_node_desc_t &m);
@@ -95,7 +97,8 @@ class Scene final : public SceneBase {
     void RebuildTexViews_nolock();
 
   public:
-    explicit Scene(ILog *log);
+    // build_ctx: device context the fast (LBVH) mesh build runs on (mesh_desc_t::use_fast_bvh_build)
+    explicit Scene(ILog *log, rc_ctx *build_ctx = nullptr);
     ~Scene() override;
 
     void GetEnvironment(environment_desc_t &env) override;

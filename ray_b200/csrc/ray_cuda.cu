@@ -23,6 +23,7 @@
 #include "rt_denoise.cuh"
 #include "rt_unet.cuh"
 #include "rt_unet_tc.cuh"
+#include "rt_lbvh.cuh"
 
 using namespace rt;
 
@@ -1560,6 +1561,65 @@ int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags) 
         ctx->stats_us[8] += uint64_t(double(ms) * 1000.0);
     }
     return 0;
+}
+
+int rc_build_lbvh(rc_ctx *ctx, const float *boxes, uint32_t n, rc_lbvh_node *nodes_out, uint32_t *order_out) {
+    if (!ctx || !boxes || !nodes_out || !order_out || n < 2 || n > 0x3fffffffu) {
+        return fail(ctx, "rc_build_lbvh: bad argument");
+    }
+    static_assert(sizeof(rc_lbvh_node) == sizeof(LbvhNode), "layout");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    float *d_boxes = nullptr, *d_bounds = nullptr;
+    uint32_t *d_codes = nullptr, *d_codes2 = nullptr, *d_ids = nullptr, *d_ids2 = nullptr, *d_parent = nullptr, *d_visits = nullptr;
+    LbvhNode *d_nodes = nullptr;
+    void *d_temp = nullptr;
+    size_t temp_bytes = 0;
+    int rc = 1;
+    do {
+        if (cudaMalloc(&d_boxes, size_t(n) * 6 * sizeof(float)) != cudaSuccess || cudaMalloc(&d_bounds, 6 * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&d_codes, n * 4) != cudaSuccess || cudaMalloc(&d_codes2, n * 4) != cudaSuccess ||
+            cudaMalloc(&d_ids, n * 4) != cudaSuccess || cudaMalloc(&d_ids2, n * 4) != cudaSuccess ||
+            cudaMalloc(&d_parent, (size_t(2) * n - 1) * 4) != cudaSuccess || cudaMalloc(&d_visits, size_t(n) * 4) != cudaSuccess ||
+            cudaMalloc(&d_nodes, (size_t(2) * n - 1) * sizeof(LbvhNode)) != cudaSuccess) {
+            fail(ctx, "rc_build_lbvh: out of device memory");
+            break;
+        }
+        cudaMemcpyAsync(d_boxes, boxes, size_t(n) * 6 * sizeof(float), cudaMemcpyHostToDevice, s);
+        const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, int(0x80000000), int(0x80000000), int(0x80000000)};
+        cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(d_visits, 0, size_t(n) * 4, s);
+        const unsigned blocks = (n + 255) / 256;
+        k_lbvh_bounds<<<min(blocks, 1024u), 256, 0, s>>>(d_boxes, n, d_bounds);
+        k_lbvh_codes<<<blocks, 256, 0, s>>>(d_boxes, n, d_bounds, d_codes, d_ids);
+        cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_codes, d_codes2, d_ids, d_ids2, int(n), 0, 30, s);
+        if (cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 16) != cudaSuccess) {
+            fail(ctx, "rc_build_lbvh: out of device memory");
+            break;
+        }
+        cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_codes, d_codes2, d_ids, d_ids2, int(n), 0, 30, s);
+        k_lbvh_hierarchy<<<blocks, 256, 0, s>>>(d_codes2, int(n), d_nodes, d_parent);
+        k_lbvh_fit<<<blocks, 256, 0, s>>>(d_boxes, d_ids2, int(n), d_nodes, d_parent, d_visits);
+        cudaMemcpyAsync(nodes_out, d_nodes, (size_t(2) * n - 1) * sizeof(LbvhNode), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(order_out, d_ids2, size_t(n) * 4, cudaMemcpyDeviceToHost, s);
+        const cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            fail(ctx, "rc_build_lbvh: %s", cudaGetErrorString(e));
+            break;
+        }
+        rc = 0;
+    } while (false);
+    cudaFree(d_boxes);
+    cudaFree(d_bounds);
+    cudaFree(d_codes);
+    cudaFree(d_codes2);
+    cudaFree(d_ids);
+    cudaFree(d_ids2);
+    cudaFree(d_parent);
+    cudaFree(d_visits);
+    cudaFree(d_nodes);
+    cudaFree(d_temp);
+    return rc;
 }
 
 int rc_denoise_nlm(rc_ctx *ctx, const rc_rect *rect, int iteration) {

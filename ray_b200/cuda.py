@@ -68,6 +68,7 @@ def load_library():
         "rc_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, P(C.c_float)]),
         "rc_readback_async": (C.c_int, [vp, C.c_int, P(capi.rc_rect), vp, C.c_int]),
         "rc_unet_set_weights": (C.c_int, [vp, vp]),
+        "rc_build_lbvh": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
         "rc_denoise_unet": (C.c_int, [vp, C.c_int, P(capi.rc_rect), C.c_uint32]),
         "rc_comm_init": (C.c_int, [P(vp), C.c_int, P(vp)]),
         "rc_comm_destroy": (None, [vp]),
@@ -97,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
     "rc_event_record", "rc_event_elapsed_ms", "rc_readback_async", "rc_comm_init", "rc_comm_destroy", "rc_comm_last_error",
     "rc_comm_strip", "rc_comm_upload_scene", "rc_comm_upload_tables", "rc_comm_render", "rc_comm_sync", "rc_gather",
-    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet",
+    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet", "rc_build_lbvh",
 ]
 
 
@@ -184,6 +185,19 @@ class Context:
     def denoise_unet(self, rect, flags=0, pass_index=-1):
         r = capi.rc_rect(*rect)
         self._check(self.lib.rc_denoise_unet(self._ctx, pass_index, C.byref(r), flags), "rc_denoise_unet")
+
+    LBVH_NODE = np.dtype([("mn", "<f4", 3), ("mx", "<f4", 3), ("left", "<u4"), ("right", "<u4"), ("first", "<u4"),
+                          ("count", "<u4")])
+
+    def build_lbvh(self, boxes):
+        """boxes: (n, 6) float32 {min xyz, max xyz}.  Returns (nodes[2n-1] of LBVH_NODE, order[n])."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        n = boxes.shape[0]
+        nodes = np.zeros(2 * n - 1, dtype=self.LBVH_NODE)
+        order = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.rc_build_lbvh(self._ctx, boxes.ctypes.data, n, nodes.ctypes.data, order.ctypes.data),
+                    "rc_build_lbvh")
+        return nodes, order
 
     def denoise_nlm(self, rect, iteration):
         r = capi.rc_rect(*rect)
