@@ -178,6 +178,16 @@ enum { RC_UNET_TENSOR_CORES = 0, RC_UNET_FP32 = 1 };
 int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]);
 int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags);
 
+/* Incremental scene update for animated instance transforms (reference: Cpu::Scene::SetMeshInstanceTransform ->
+ * RebuildTLAS_nolock, SceneCPU.cpp:884-905 / 1021-1056): re-reads from `scene` ONLY the top-level nodes
+ * wnodes[first_tlas_node ..), mesh_instances, lights, light_cwnodes, the light counts, tlas_root and the bounds; every
+ * other array (BLAS nodes below first_tlas_node, triangles, vertices, materials, textures, environment) is taken to be
+ * what the last rc_upload_scene got and is neither read nor copied.  The node count may differ from the uploaded one
+ * (a rebuilt top level rarely has the same size); the instance count may not.  Blocking. */
+int rc_update_instances(rc_ctx *ctx, const rc_scene_view *scene, uint32_t first_tlas_node);
+/* Cumulative host->device bytes rc_upload_scene and rc_update_instances have copied on this context. */
+uint64_t rc_scene_upload_bytes(const rc_ctx *ctx);
+
 /* Device build of a binary BVH over n primitive boxes (the fast builder of SURVEY.md section 8(f) row 4; reference:
  * PreprocessPrims_HLBVH, internal/Core.cpp:574-720): Morton order of the box centroids, Karras' parallel radix tree,
  * bottom-up box fit.  boxes: n x {min xyz, max xyz}.  nodes_out: 2n - 1 records {min[3], max[3], left, right, first,

@@ -46,6 +46,10 @@ uint32_t rh_add_material_node(rh_scene *s, const rs_shading_node_desc *d);
 uint32_t rh_add_material_principled(rh_scene *s, const rs_principled_mat_desc *d);
 uint32_t rh_add_mesh(rh_scene *s, const rs_mesh_desc *d);
 uint32_t rh_add_mesh_instance(rh_scene *s, const rs_mesh_instance_desc *d);
+/* SceneBase::SetMeshInstanceTransform / RemoveMeshInstance (take effect at the next rh_finalize; a Finalize that follows
+ * only transform / analytic-light edits makes the renderer refresh the top level alone: rc_update_instances) */
+void rh_set_mesh_instance_transform(rh_scene *s, uint32_t instance, const float *xform /* 16, column-major as in the desc */);
+void rh_remove_mesh_instance(rh_scene *s, uint32_t instance);
 uint32_t rh_add_light_directional(rh_scene *s, const rs_directional_light_desc *d);
 uint32_t rh_add_light_sphere(rh_scene *s, const rs_sphere_light_desc *d);
 uint32_t rh_add_light_spot(rh_scene *s, const rs_spot_light_desc *d);

@@ -230,14 +230,19 @@ bool Renderer::Prepare(const Scene &s, const camera_t &cam) {
     if (uploaded_scene_ != &s || uploaded_revision_ != s.revision()) {
         rc_scene_view v;
         s.FillView(v);
+        // only instance transforms / lights moved since the upload: refresh the top level, keep the geometry in HBM
+        const bool top_level_only = uploaded_scene_ == &s && uploaded_structure_ == s.structure_revision();
         for (rc_ctx *c : ctxs_) { // replicated: every band needs the whole scene
-            if (rc_upload_scene(c, &v) != 0) {
+            const int rc = top_level_only ? rc_update_instances(c, &v, s.first_tlas_node()) : rc_upload_scene(c, &v);
+            if (rc != 0) {
                 log_->Error("Ray(CUDA): %s", rc_last_error(c));
+                uploaded_scene_ = nullptr;
                 return false;
             }
         }
         uploaded_scene_ = &s;
         uploaded_revision_ = s.revision();
+        uploaded_structure_ = s.structure_revision();
     }
     return true;
 }

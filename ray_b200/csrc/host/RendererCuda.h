@@ -32,6 +32,7 @@ class Renderer final : public RendererBase {
 
     const Scene *uploaded_scene_ = nullptr;
     uint64_t uploaded_revision_ = 0;
+    uint64_t uploaded_structure_ = 0;
     uint32_t filter_table_filter_ = 0xffffffffu;
     float filter_table_width_ = 0.0f;
     std::vector<uint32_t> sampler_table_;

@@ -264,6 +264,7 @@ void Scene::GetEnvironment(environment_desc_t &env) {
 }
 void Scene::SetEnvironment(const environment_desc_t &env) {
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     env_ = env;
 }
 
@@ -317,6 +318,7 @@ TextureHandle Scene::AddTexture(const tex_desc_t &t) {
         return TextureHandle{};
     }
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     const uint32_t index = tex_storage_counts_[storage]++;
     img.handle = (uint32_t(storage) << 28) | index;
     uint32_t ret = img.handle;
@@ -373,6 +375,7 @@ MaterialHandle Scene::AddMaterial_nolock(const shading_node_desc_t &m) {
 
 MaterialHandle Scene::AddMaterial(const shading_node_desc_t &m) {
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     return AddMaterial_nolock(m);
 }
 
@@ -404,6 +407,7 @@ MaterialHandle Scene::AddMaterial(const principled_mat_desc_t &m) {
     mm.clearcoat_roughness_unorm = pack_unorm_16(clampf(m.clearcoat_roughness, 0.0f, 1.0f));
 
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     materials_.push_back(mm);
     MaterialHandle root{uint32_t(materials_.size() - 1), 0};
     MaterialHandle emissive, transparent;
@@ -560,6 +564,7 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
     const uint32_t n_tris = uint32_t(m.vtx_indices_count / 3);
 
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     if (tlas_root_ != 0xffffffffu) { // drop the TLAS appended by a previous Finalize
         wnodes_.resize(blas_nodes_end_);
         tlas_root_ = 0xffffffffu;
@@ -734,6 +739,7 @@ MeshHandle Scene::AddMesh(const mesh_desc_t &m) {
 
 void Scene::RemoveMesh(MeshHandle m) {
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     if (m._index < meshes_.size()) {
         meshes_[m._index].alive = false;
         for (size_t i = 0; i < mesh_instances_.size(); ++i) {
@@ -884,6 +890,7 @@ void Scene::RemoveLight(LightHandle l) {
 // reference SceneCPU.cpp:770-863
 MeshInstanceHandle Scene::AddMeshInstance(const mesh_instance_desc_t &d) {
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     if (d.mesh >= meshes_.size() || !meshes_[d.mesh].alive) {
         log_->Error("Ray(CUDA): AddMeshInstance: unknown mesh %u", d.mesh);
         return MeshInstanceHandle{};
@@ -973,6 +980,7 @@ void Scene::RemoveMeshInstance_nolock(uint32_t index) {
 
 void Scene::RemoveMeshInstance(MeshInstanceHandle h) {
     std::unique_lock<std::shared_timed_mutex> lock(mtx_);
+    structure_dirty_ = true;
     RemoveMeshInstance_nolock(h._index);
 }
 
@@ -1081,6 +1089,10 @@ void Scene::Finalize(const ParallelFor &) {
     RebuildLightTree_nolock();
     GetBounds(bounds_min_, bounds_max_);
     revision_ = NextRevision();
+    if (structure_dirty_) { // anything but instance transforms / analytic lights changed: the renderer uploads everything
+        structure_revision_ = revision_;
+        structure_dirty_ = false;
+    }
     RebuildTexViews_nolock();
     RefreshPinnedMirrors_nolock();
 }

@@ -86,6 +86,10 @@ class Scene final : public SceneBase {
     // process-wide unique, so (scene address, revision) never repeats for a new scene at a recycled address
     static uint64_t NextRevision();
     mutable uint64_t revision_ = NextRevision(); // renewed by Finalize: tells the renderer to re-upload
+    // revision at which geometry / materials / textures / environment / the instance set last changed: a Finalize that
+    // only follows SetMeshInstanceTransform or light edits keeps it, and the renderer refreshes the top level only
+    uint64_t structure_revision_ = 0;
+    bool structure_dirty_ = true;
 
     rc_ctx *build_ctx_ = nullptr;
 
@@ -133,6 +137,8 @@ class Scene final : public SceneBase {
     // what Cuda::Renderer hands to rc_upload_scene
     void FillView(rc_scene_view &v) const;
     uint64_t revision() const { return revision_; }
+    uint64_t structure_revision() const { return structure_revision_; }
+    uint32_t first_tlas_node() const { return blas_nodes_end_; }
     bool GetDeviceCamera(rc_camera &out) const; // the flattened camera_t RenderScene passes to rc_render
     void GetBounds(float bbox_min[3], float bbox_max[3]) const;
 };

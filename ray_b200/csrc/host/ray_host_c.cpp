@@ -91,6 +91,16 @@ uint32_t rh_add_material_node(rh_scene *s, const rs_shading_node_desc *d) { retu
 uint32_t rh_add_material_principled(rh_scene *s, const rs_principled_mat_desc *d) { return S(s)->AddMaterial(*d)._index; }
 uint32_t rh_add_mesh(rh_scene *s, const rs_mesh_desc *d) { return S(s)->AddMesh(*d)._index; }
 uint32_t rh_add_mesh_instance(rh_scene *s, const rs_mesh_instance_desc *d) { return S(s)->AddMeshInstance(*d)._index; }
+void rh_set_mesh_instance_transform(rh_scene *s, uint32_t instance, const float *xform) {
+    MeshInstanceHandle h;
+    h._index = instance;
+    S(s)->SetMeshInstanceTransform(h, xform);
+}
+void rh_remove_mesh_instance(rh_scene *s, uint32_t instance) {
+    MeshInstanceHandle h;
+    h._index = instance;
+    S(s)->RemoveMeshInstance(h);
+}
 uint32_t rh_add_light_directional(rh_scene *s, const rs_directional_light_desc *d) { return S(s)->AddLight(*d)._index; }
 uint32_t rh_add_light_sphere(rh_scene *s, const rs_sphere_light_desc *d) { return S(s)->AddLight(*d)._index; }
 uint32_t rh_add_light_spot(rh_scene *s, const rs_spot_light_desc *d) { return S(s)->AddLight(*d)._index; }

@@ -89,6 +89,8 @@ struct rc_ctx {
     bool have_scene = false;
     rc_scene_view scene_info{};
     uint32_t li_count = 0;
+    uint64_t scene_h2d_bytes = 0; // host->device bytes rc_upload_scene / rc_update_instances have copied so far
+    std::map<uint32_t, uint32_t> tex_dense; // (storage << 28 | index) -> dense texture id of the uploaded scene
 
     bool stats_enabled = true;
     std::vector<cudaEvent_t> events;
@@ -162,6 +164,7 @@ int upload_array(rc_ctx *ctx, DevArray &dst, const rc_array &src, uint32_t expec
         return 0;
     }
     CU_CHECK(ctx, cudaMemcpyAsync(dst.ptr, src.ptr, dst.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->scene_h2d_bytes += dst.bytes;
     return 0;
 }
 
@@ -404,7 +407,7 @@ int build_traversal_copies(rc_ctx *ctx, const rc_scene_view *sv) {
     }
     if (n_nodes != 0) {
         k_build_dnodes<<<(n_nodes * 8 + 255) / 256, 256, 0, ctx->stream>>>(
-            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<WNode *>(ctx->dnodes.ptr), n_nodes);
+            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<WNode *>(ctx->dnodes.ptr), 0u, n_nodes);
     }
     if (n_inst != 0) {
         k_build_blas_roots<<<(n_inst + 255) / 256, 256, 0, ctx->stream>>>(
@@ -1172,11 +1175,161 @@ int rc_upload_scene(rc_ctx *ctx, const rc_scene_view *sv) {
         q = nullptr;
     }
     ctx->li_count = sv->li_indices.count;
+    ctx->tex_dense = dense;
     set_sort_bounds(ctx->sort, sv->bounds_min, sv->bounds_max);
     if (build_traversal_copies(ctx, sv)) {
         return 1;
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_scene = true;
+    return 0;
+}
+
+namespace {
+// grow / shrink a node array to new_count records keeping the first `keep` ones (device-to-device)
+int resize_keep(rc_ctx *ctx, DevArray &a, uint32_t keep, uint32_t new_count) {
+    const size_t want = size_t(new_count) * sizeof(WNode);
+    if (a.ptr && a.bytes == want) {
+        return 0;
+    }
+    void *fresh = nullptr;
+    CU_CHECK(ctx, cudaMalloc(&fresh, want ? want : 256));
+    if (a.ptr && keep != 0) {
+        CU_CHECK(ctx, cudaMemcpyAsync(fresh, a.ptr, size_t(keep) * sizeof(WNode), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(a.ptr);
+    a.ptr = fresh;
+    a.bytes = want;
+    a.count = new_count;
+    return 0;
+}
+} // namespace
+
+uint64_t rc_scene_upload_bytes(const rc_ctx *ctx) { return ctx ? ctx->scene_h2d_bytes : 0; }
+
+int rc_update_instances(rc_ctx *ctx, const rc_scene_view *sv, uint32_t first_node) {
+    if (!ctx || !sv) {
+        return fail(ctx, "rc_update_instances: null argument");
+    }
+    if (!ctx->have_scene) {
+        return fail(ctx, "rc_update_instances: no scene uploaded");
+    }
+    cudaSetDevice(ctx->device);
+    const rc_scene_view &old = ctx->scene_info;
+    const uint32_t n_nodes = sv->wnodes.count, n_inst = sv->mesh_instances.count;
+    if (sv->mtris.count != old.mtris.count || sv->tri_indices.count != old.tri_indices.count ||
+        sv->tri_materials.count != old.tri_materials.count || sv->materials.count != old.materials.count ||
+        sv->vertices.count != old.vertices.count || sv->vtx_indices.count != old.vtx_indices.count ||
+        sv->texture_count != old.texture_count || n_inst != old.mesh_instances.count) {
+        return fail(ctx, "rc_update_instances: geometry, materials or the instance count changed since rc_upload_scene");
+    }
+    if (first_node > n_nodes || first_node > old.wnodes.count || sv->wnodes.stride != sizeof(WNode) ||
+        (n_inst != 0 && sv->mesh_instances.stride != sizeof(MeshInstance)) ||
+        (sv->lights.count != 0 && (sv->lights.stride != sizeof(Light) || !sv->lights.ptr)) ||
+        (n_nodes != 0 && !sv->wnodes.ptr) || (n_inst != 0 && !sv->mesh_instances.ptr)) {
+        return fail(ctx, "rc_update_instances: bad node range or array strides");
+    }
+    // ---- validate the new top level: nodes [first_node, n_nodes) reference each other or mesh instances only ----
+    const WNode *nodes = static_cast<const WNode *>(sv->wnodes.ptr);
+    const MeshInstance *inst = static_cast<const MeshInstance *>(sv->mesh_instances.ptr);
+    uint32_t root_word = kEmptyChild;
+    if (sv->tlas_root != 0xffffffffu) {
+        if (sv->tlas_root < first_node || sv->tlas_root >= n_nodes) {
+            return fail(ctx, "rc_update_instances: tlas_root %u outside [%u, %u)", sv->tlas_root, first_node, n_nodes);
+        }
+        for (uint32_t n = first_node; n < n_nodes; ++n) {
+            const WNode &nd = nodes[n];
+            if (nd.child[0] & kLeafBit) {
+                const uint32_t first = nd.child[0] & kPrimIndexBits;
+                if (first >= n_inst || inst[first].node_index >= first_node) {
+                    return fail(ctx, "rc_update_instances: top-level leaf %u names instance %u (of %u) or a BLAS root past %u",
+                                n, first, n_inst, first_node);
+                }
+                continue;
+            }
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t ch = nd.child[c];
+                if (ch != kEmptyChild && (ch < first_node || ch >= n_nodes)) {
+                    return fail(ctx, "rc_update_instances: top-level node %u child %d = %u outside [%u, %u)", n, c, ch,
+                                first_node, n_nodes);
+                }
+            }
+        }
+        const uint32_t c0 = nodes[sv->tlas_root].child[0], c1 = nodes[sv->tlas_root].child[1];
+        if (c0 & kLeafBit) {
+            const uint32_t first = c0 & kPrimIndexBits, blocks = ((first & 7u) + c1 + 7u) / 8u;
+            if (first >= kLeafFirstBits || blocks == 0 || blocks > 16) {
+                return fail(ctx, "rc_update_instances: the TLAS root leaf cannot be encoded");
+            }
+            root_word = kLeafBit | ((blocks - 1u) << kLeafBlocksShift) | first;
+        } else {
+            root_word = sv->tlas_root;
+        }
+    }
+    // ---- lights: texture handles of triangle lights -> dense ids of the uploaded texture table ----
+    std::vector<Light> lts;
+    if (sv->lights.count != 0) {
+        const Light *l = static_cast<const Light *>(sv->lights.ptr);
+        lts.assign(l, l + sv->lights.count);
+        for (uint32_t i = 0; i < lts.size(); ++i) {
+            if ((lts[i].bits & 7u) == LIGHT_TRI) {
+                uint32_t h;
+                memcpy(&h, &lts[i].p[2], 4);
+                if (h != 0xffffffffu) {
+                    const auto it = ctx->tex_dense.find(h & 0xf0ffffffu);
+                    if (it == ctx->tex_dense.end()) {
+                        return fail(ctx, "rc_update_instances: triangle light %u references texture 0x%08x which was not uploaded", i, h);
+                    }
+                    h = (h & 0x0f000000u) | it->second;
+                    memcpy(&lts[i].p[2], &h, 4);
+                }
+            }
+        }
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // samples in flight still read the old top level
+    ctx->have_scene = false;
+    if (resize_keep(ctx, ctx->wnodes, first_node, n_nodes) || resize_keep(ctx, ctx->dnodes, first_node, n_nodes)) {
+        return 1;
+    }
+    ctx->wnodes.count = ctx->dnodes.count = n_nodes;
+    if (n_nodes > first_node) {
+        CU_CHECK(ctx, cudaMemcpyAsync(static_cast<WNode *>(ctx->wnodes.ptr) + first_node, nodes + first_node,
+                                      size_t(n_nodes - first_node) * sizeof(WNode), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->scene_h2d_bytes += size_t(n_nodes - first_node) * sizeof(WNode);
+    }
+    rc_array la = sv->lights;
+    la.ptr = lts.data();
+    if (upload_array(ctx, ctx->mesh_instances, sv->mesh_instances, sizeof(MeshInstance), "mesh_instances") ||
+        upload_array(ctx, ctx->lights, la, sizeof(Light), "lights") ||
+        upload_array(ctx, ctx->light_cwnodes, sv->light_cwnodes, sizeof(LightCWNode), "light_cwnodes")) {
+        return 1;
+    }
+    if (n_nodes > first_node) {
+        k_build_dnodes<<<((n_nodes - first_node) * 8 + 255) / 256, 256, 0, ctx->stream>>>(
+            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<WNode *>(ctx->dnodes.ptr), first_node, n_nodes);
+    }
+    if (n_inst != 0) {
+        k_build_blas_roots<<<(n_inst + 255) / 256, 256, 0, ctx->stream>>>(
+            static_cast<const WNode *>(ctx->wnodes.ptr), static_cast<const MeshInstance *>(ctx->mesh_instances.ptr), n_inst,
+            n_nodes, static_cast<uint32_t *>(ctx->blas_roots.ptr));
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // lts is a local
+    CU_CHECK(ctx, cudaGetLastError());
+    ctx->tlas_root_word = root_word;
+    rc_scene_view &info = ctx->scene_info;
+    info.wnodes.count = n_nodes;
+    info.lights.count = sv->lights.count;
+    info.li_indices.count = sv->li_indices.count;
+    info.light_cwnodes.count = sv->light_cwnodes.count;
+    info.tlas_root = sv->tlas_root;
+    info.visible_lights_count = sv->visible_lights_count;
+    info.blocker_lights_count = sv->blocker_lights_count;
+    info.env_light_index = sv->env_light_index;
+    memcpy(info.bounds_min, sv->bounds_min, sizeof(info.bounds_min));
+    memcpy(info.bounds_max, sv->bounds_max, sizeof(info.bounds_max));
+    ctx->li_count = sv->li_indices.count;
+    set_sort_bounds(ctx->sort, sv->bounds_min, sv->bounds_max);
     ctx->have_scene = true;
     return 0;
 }

@@ -85,9 +85,9 @@ RT_DEV uint32_t leaf_word(uint32_t c0, uint32_t c1) {
     return kLeafBit | ((blocks - 1u) << kLeafBlocksShift) | first;
 }
 
-__global__ void k_build_dnodes(const WNode *__restrict__ src, WNode *__restrict__ dst, uint32_t count) {
+__global__ void k_build_dnodes(const WNode *__restrict__ src, WNode *__restrict__ dst, uint32_t first, uint32_t count) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = gid >> 3, c = gid & 7u;
+    const uint32_t n = first + (gid >> 3), c = gid & 7u; // nodes [first, count): a TLAS-only refresh starts past the BLASes
     if (n >= count) {
         return;
     }

@@ -69,6 +69,8 @@ def load_library():
         "rc_readback_async": (C.c_int, [vp, C.c_int, P(capi.rc_rect), vp, C.c_int]),
         "rc_unet_set_weights": (C.c_int, [vp, vp]),
         "rc_build_lbvh": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "rc_update_instances": (C.c_int, [vp, vp, C.c_uint32]),
+        "rc_scene_upload_bytes": (C.c_uint64, [vp]),
         "rc_denoise_unet": (C.c_int, [vp, C.c_int, P(capi.rc_rect), C.c_uint32]),
         "rc_comm_init": (C.c_int, [P(vp), C.c_int, P(vp)]),
         "rc_comm_destroy": (None, [vp]),
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
     "rc_event_record", "rc_event_elapsed_ms", "rc_readback_async", "rc_comm_init", "rc_comm_destroy", "rc_comm_last_error",
     "rc_comm_strip", "rc_comm_upload_scene", "rc_comm_upload_tables", "rc_comm_render", "rc_comm_sync", "rc_gather",
-    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet", "rc_build_lbvh",
+    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet", "rc_build_lbvh", "rc_update_instances", "rc_scene_upload_bytes",
 ]
 
 
@@ -157,6 +159,12 @@ class Context:
 
     def upload_scene(self, view: capi.rc_scene_view):
         self._check(self.lib.rc_upload_scene(self._ctx, C.byref(view)), "rc_upload_scene")
+
+    def update_instances(self, view: capi.rc_scene_view, first_tlas_node):
+        self._check(self.lib.rc_update_instances(self._ctx, C.byref(view), first_tlas_node), "rc_update_instances")
+
+    def scene_upload_bytes(self):
+        return int(self.lib.rc_scene_upload_bytes(self._ctx))
 
     def make_pass(self, cam: capi.rc_camera, rect, iteration, flags=0):
         p = capi.rc_pass_desc()

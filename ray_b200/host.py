@@ -23,7 +23,8 @@ FINAL, RAW, BASE_COLOR, DEPTH_NORMALS = 0, 1, 2, 3
 EXPORTED_SYMBOLS = [
     "rh_create_renderer", "rh_create_renderer_multi", "rh_device_count", "rh_set_unet_weights", "rh_denoise_unet", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
     "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_denoise", "rh_add_texture", "rh_add_material_node",
-    "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_add_light_directional",
+    "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_set_mesh_instance_transform",
+    "rh_remove_mesh_instance", "rh_add_light_directional",
     "rh_add_light_sphere", "rh_add_light_spot", "rh_add_light_rect", "rh_add_light_disk", "rh_add_light_line",
     "rh_add_camera", "rh_finalize", "rh_triangle_count", "rh_node_count", "rh_scene_view", "rh_get_camera", "rh_render",
     "rh_get_pixels", "rh_get_stats", "rh_reset_stats", "rh_get_counters", "rh_get_kernel_ms", "rh_set_sampler_table",
@@ -64,6 +65,8 @@ def load_library():
         "rh_add_material_principled": (u32, [vp, P(capi.rs_principled_mat_desc)]),
         "rh_add_mesh": (u32, [vp, P(capi.rs_mesh_desc)]),
         "rh_add_mesh_instance": (u32, [vp, P(capi.rs_mesh_instance_desc)]),
+        "rh_set_mesh_instance_transform": (None, [vp, u32, vp]),
+        "rh_remove_mesh_instance": (None, [vp, u32]),
         "rh_add_light_directional": (u32, [vp, P(capi.rs_directional_light_desc)]),
         "rh_add_light_sphere": (u32, [vp, P(capi.rs_sphere_light_desc)]),
         "rh_add_light_spot": (u32, [vp, P(capi.rs_spot_light_desc)]),
@@ -182,6 +185,13 @@ class Scene:
                                        refraction_visibility=int(refraction_visibility),
                                        shadow_visibility=int(shadow_visibility))
         return self.lib.rh_add_mesh_instance(self.h, C.byref(d))
+
+    def set_mesh_instance_transform(self, instance, xform):
+        m = np.ascontiguousarray(xform, dtype=np.float32).reshape(16)
+        self.lib.rh_set_mesh_instance_transform(self.h, instance, m.ctypes.data)
+
+    def remove_mesh_instance(self, instance):
+        self.lib.rh_remove_mesh_instance(self.h, instance)
 
     def add_light(self, kind, d):
         return getattr(self.lib, f"rh_add_light_{kind}")(self.h, C.byref(d))

@@ -142,3 +142,44 @@ def test_unsupported_features_are_reported_not_faked():
         r.check()
     s.close()
     r.close()
+
+
+def test_moved_instances_refresh_only_the_top_level(oracle_mod):
+    """SetMeshInstanceTransform + Finalize: the renderer re-sends the TLAS, instance and light records only
+    (rc_update_instances), and the image equals the one a complete upload of the same scene state gives, bit for bit."""
+    from ray_b200 import cuda
+    desc = scenes.instanced(25, 3000, 160, 120)
+    w, h = desc.width, desc.height
+    r = host.Renderer(w, h)
+    r.set_sampler_table(oracle_mod.pmj_table())
+    lib = cuda.load_library()
+    ctx = r.native_context()
+    s = scenes.build(desc, r.create_scene())
+    r.render(s, (0, 0, w, h), 0, 2)
+    one_full = total = lib.rc_scene_upload_bytes(ctx)
+    assert one_full > 0
+    before = r.pixels(host.RAW)
+
+    for step in range(1, 4):  # a few animation frames
+        for i in (1, 7, 13):
+            x = np.asarray(desc.instances[i][1], dtype=np.float32).reshape(4, 4).copy()
+            x[3, :3] += np.float32(0.15 * step)  # column-major: translation lives in the last column = row 3 here
+            s.set_mesh_instance_transform(i, x)
+        s.finalize()
+        r.clear()
+        r.render(s, (0, 0, w, h), 0, 2)
+        moved = r.pixels(host.RAW)
+        sent = lib.rc_scene_upload_bytes(ctx) - total
+        assert 0 < sent < 0.05 * one_full, "a transform edit re-sent the geometry"
+        total += sent
+        r.invalidate_scene()  # complete upload of the same state
+        r.clear()
+        r.render(s, (0, 0, w, h), 0, 2)
+        again = r.pixels(host.RAW)
+        sent = lib.rc_scene_upload_bytes(ctx) - total
+        assert sent >= 0.9 * one_full
+        total += sent
+        assert np.array_equal(moved.view(np.uint32), again.view(np.uint32))
+        assert not np.array_equal(moved, before)
+    s.close()
+    r.close()

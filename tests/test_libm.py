@@ -96,7 +96,7 @@ def test_device_expf_restatement_matches_host_libm(tmp_path):
     the filter produces (<= 0) plus positive and overflow / underflow edge cases."""
     src = open(os.path.join(ROOT, "ray_b200", "csrc", "rt_math.cuh")).read()
     i0 = src.index("RT_FN float libm_expf(float x) {")
-    i1 = src.index("// exp2f(float(e) - 128.0f) of rgbe_to_rgb")
+    i1 = src.index("// logf and powf of the host libm (glibc 2.39")
     code = src[i0:i1].replace("RT_FN", "static")
     c = r'''
 #include <math.h>
