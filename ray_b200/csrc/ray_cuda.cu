@@ -78,7 +78,7 @@ struct rc_ctx {
     // tensor-core path (rt_unet_tc.cuh): fp16 weights [9][n][in_cs], fp32 biases [n], bordered fp16 tensors
     __half *unet_hw[kUNetLayers] = {};
     float *unet_hb[kUNetLayers] = {};
-    __half *unet_ht[15] = {}, *unet_hx0 = nullptr, *unet_hs = nullptr, *unet_hg = nullptr;
+    __half *unet_ht[15] = {}, *unet_hx0 = nullptr, *unet_hs = nullptr;
     int unet_htw = 0, unet_hth = 0;
     void *tensor_map_encode = nullptr; // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint
     float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
@@ -874,7 +874,6 @@ void rc_destroy(rc_ctx *ctx) {
     }
     cudaFree(ctx->unet_hx0);
     cudaFree(ctx->unet_hs);
-    cudaFree(ctx->unet_hg);
     for (DevArray *a : {&ctx->dnodes, &ctx->blas_roots, &ctx->dmtris, &ctx->wnodes, &ctx->mtris, &ctx->tri_indices, &ctx->tri_materials, &ctx->materials,
                         &ctx->mesh_instances, &ctx->vertices, &ctx->vtx_indices, &ctx->lights, &ctx->light_cwnodes,
                         &ctx->tex_descs, &ctx->tex_texels, &ctx->qtree}) {
@@ -1413,15 +1412,17 @@ int unet_alloc_tensors(rc_ctx *ctx) {
 namespace {
 int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
 
-// real (16-padded) input channels of layer i on the tensor-core path and the position of original input channel ci
-int unet_tc_cin(int i) {
-    const UNetLayerShape L = unet_layer(i);
-    return round_up_i(L.cin1, 16) + (L.cin2 ? round_up_i(L.cin2, 16) : 0);
-}
+// K layout of layer i on the tensor-core path: the first input tensor's channels in nkb1 blocks of 64, then (decoder
+// layers) the skip tensor's channels in nkb2 blocks; real channels are padded to 16 inside their last block
+int unet_tc_nkb1(int i) { return (round_up_i(unet_layer(i).cin1, 16) + 63) / 64; }
+int unet_tc_nkb2(int i) { return unet_layer(i).cin2 ? (round_up_i(unet_layer(i).cin2, 16) + 63) / 64 : 0; }
+int unet_tc_in_cs(int i) { return (unet_tc_nkb1(i) + unet_tc_nkb2(i)) * 64; }
 int unet_tc_cin_pos(int i, int ci) {
     const UNetLayerShape L = unet_layer(i);
-    return ci < L.cin1 ? ci : round_up_i(L.cin1, 16) + (ci - L.cin1);
+    return ci < L.cin1 ? ci : unet_tc_nkb1(i) * 64 + (ci - L.cin1);
 }
+// layers whose output feeds a decoder's up-sampling: they write every pixel to a 2 x 2 block of the finer grid
+bool unet_tc_writes_upsampled(int i) { return i + 1 < kUNetLayers && unet_layer(i + 1).up; }
 
 size_t unet_h_elems(int w, int h, int cs) { return size_t(w + 2) * size_t(h + 2) * size_t(cs); }
 
@@ -1436,8 +1437,7 @@ int unet_tc_alloc(rc_ctx *ctx) {
     }
     cudaFree(ctx->unet_hx0);
     cudaFree(ctx->unet_hs);
-    cudaFree(ctx->unet_hg);
-    ctx->unet_hx0 = ctx->unet_hs = ctx->unet_hg = nullptr;
+    ctx->unet_hx0 = ctx->unet_hs = nullptr;
     ctx->unet_htw = ctx->unet_hth = 0;
     auto alloc0 = [&](__half **p, size_t n) -> int {
         CU_CHECK(ctx, cudaMalloc(p, n * sizeof(__half)));
@@ -1447,13 +1447,15 @@ int unet_tc_alloc(rc_ctx *ctx) {
     for (int i = 0; i < 15; ++i) {
         int c, sh;
         unet_tensor_shape(i, c, sh);
+        if (unet_tc_writes_upsampled(i)) {
+            --sh; // stored already up-sampled (the convolution's epilogue replicates)
+        }
         if (alloc0(&ctx->unet_ht[i], unet_h_elems(wr >> sh, hr >> sh, round_up_i(c, 64)))) {
             return 1;
         }
     }
-    // network input (64), conv output before pooling (<= 128 stride at level 0..3: sized for level 0 with 128), decoder input
-    if (alloc0(&ctx->unet_hx0, unet_h_elems(wr, hr, 64)) || alloc0(&ctx->unet_hs, unet_h_elems(wr, hr, 128)) ||
-        alloc0(&ctx->unet_hg, unet_h_elems(wr, hr, 192))) {
+    // network input (64-channel stride) and the pre-pooling output of the encoder convolutions (sized for level 0)
+    if (alloc0(&ctx->unet_hx0, unet_h_elems(wr, hr, 64)) || alloc0(&ctx->unet_hs, unet_h_elems(wr, hr, 128))) {
         return 1;
     }
     ctx->unet_htw = wr;
@@ -1488,14 +1490,16 @@ int make_map(rc_ctx *ctx, CUtensorMap *m, const void *base, int cs, size_t rows,
     return 0;
 }
 
-// one convolution on the tensor cores: `in` (bordered, cin real channels, stride in_cs) -> out
-int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in, int in_cs, int cin, int w, int h, __half *out, int out_cs,
-                 const rc_rect &r) {
+// one convolution on the tensor cores: in1 (bordered, stride cs1) [++ in2 (stride cs2)] -> out
+int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in1, int cs1, const __half *in2, int cs2, int w, int h, __half *out,
+                 int out_cs, bool up, const rc_rect &r) {
     const UNetLayerShape L = unet_layer(layer);
     const int n = round_up_i(L.cout, 16);
-    CUtensorMap map_a, map_b;
-    if (make_map(ctx, &map_a, in, in_cs, size_t(w + 2) * size_t(h + 2), tc::kTileM) ||
-        make_map(ctx, &map_b, ctx->unet_hw[layer], in_cs, size_t(9) * n, n)) {
+    const size_t rows = size_t(w + 2) * size_t(h + 2);
+    CUtensorMap map_a1, map_a2, map_b;
+    if (make_map(ctx, &map_a1, in1, cs1, rows, tc::kTileM) ||
+        make_map(ctx, &map_a2, in2 ? in2 : in1, in2 ? cs2 : cs1, rows, tc::kTileM) ||
+        make_map(ctx, &map_b, ctx->unet_hw[layer], unet_tc_in_cs(layer), size_t(9) * n, n)) {
         return 1;
     }
     tc::ConvTcParams p{};
@@ -1504,23 +1508,32 @@ int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in, int in_cs, int cin, i
     p.fb = ctx->fb;
     p.w = w;
     p.h = h;
-    p.cin = cin;
-    p.in_cs = in_cs;
+    p.cin1 = round_up_i(L.cin1, 16);
+    p.nkb1 = unet_tc_nkb1(layer);
+    p.cin2 = L.cin2 ? round_up_i(L.cin2, 16) : 0;
+    p.nkb2 = unet_tc_nkb2(layer);
     p.n = n;
     p.cout = L.cout;
     p.out_cs = out_cs;
+    p.up = up ? 1 : 0;
     p.tmem_cols = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
+    const int stage_bytes = tc::kATileBytes + ((n * tc::kBlockK * 2 + 1023) & ~1023);
+    p.stages = std::min(tc::kMaxStages, tc::kSmemBudget / stage_bytes);
+    p.tiles_x = (w + tc::kTileM - 1) / tc::kTileM;
+    p.tiles = p.tiles_x * h;
     p.last = (layer == kUNetLayers - 1);
     p.rx = r.x, p.ry = r.y, p.rw = r.w, p.rh = r.h;
     p.inv_gamma = ctx->last_inv_gamma;
-    const int stage_bytes = tc::kATileBytes + ((n * tc::kBlockK * 2 + 1023) & ~1023);
-    const int smem = tc::kStages * stage_bytes + 1024;
+    // every CTA asks for the same shared memory whatever the layer: more than a third of an SM's 227 KB, so that at most
+    // two CTAs (2 x 2 accumulators of <= 128 columns = the 512 TMEM columns) are ever resident on an SM
+    const int smem = tc::kSmemBudget + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tc::k_unet_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(tc::k_unet_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
-    tc::k_unet_conv_tc<<<dim3((w + tc::kTileM - 1) / tc::kTileM, h), tc::kThreads, smem, ctx->stream>>>(map_a, map_b, p);
+    const int grid = std::min(p.tiles, 2 * ctx->num_sms);
+    tc::k_unet_conv_tc<<<grid, tc::kThreads, smem, ctx->stream>>>(map_a1, map_a2, map_b, p);
     return 0;
 }
 
@@ -1534,35 +1547,35 @@ int unet_run_tc(rc_ctx *ctx, int pass, const rc_rect &r) {
     for (int i = (pass < 0 ? 0 : pass); i <= (pass < 0 ? kUNetLayers - 1 : pass); ++i) {
         const UNetLayerShape L = unet_layer(i);
         const int w = wr >> L.level, h = hr >> L.level;
-        const __half *in;
-        int in_cs, cin = unet_tc_cin(i);
+        const __half *in1, *in2 = nullptr;
+        int cs1, cs2 = 0;
         if (i == 0) {
             tc::k_unet_feat_h<<<dim3((wr + 127) / 128, hr), 128, 0, s>>>(ctx->fb, ctx->unet_hx0, wr, hr, 64);
-            in = ctx->unet_hx0;
-            in_cs = 64;
-        } else if (L.up) {
-            // decoder: up-sample the previous tensor and append the skip tensor (or the network input)
-            const int ca = L.cin1, a_cs = round_up_i(ca, 64);
-            const __half *b = skip_of[i] == -2 ? ctx->unet_hx0 : ctx->unet_ht[skip_of[i]];
-            const int cb = skip_of[i] == -2 ? 16 : L.cin2, b_cs = skip_of[i] == -2 ? 64 : round_up_i(L.cin2, 64);
-            in_cs = round_up_i(cin, 64);
-            tc::k_unet_gather_h<<<dim3(w, h), 64, 0, s>>>(ctx->unet_ht[i - 1], a_cs, ca, b, b_cs, cb, ctx->unet_hg, in_cs, w, h);
-            in = ctx->unet_hg;
+            in1 = ctx->unet_hx0;
+            cs1 = 64;
         } else {
-            in = ctx->unet_ht[i - 1];
-            in_cs = round_up_i(L.cin1, 64);
+            // decoder (L.up): the previous layer already stored its output up-sampled; the skip tensor (or the network
+            // input) is the second K range of the same GEMM -- no gather pass
+            in1 = ctx->unet_ht[i - 1];
+            cs1 = round_up_i(L.cin1, 64);
+            if (L.up) {
+                in2 = skip_of[i] == -2 ? ctx->unet_hx0 : ctx->unet_ht[skip_of[i]];
+                cs2 = skip_of[i] == -2 ? 64 : round_up_i(L.cin2, 64);
+            }
         }
         const int out_cs = round_up_i(L.cout, 64);
         if (i == kUNetLayers - 1) {
-            if (unet_conv_tc(ctx, i, in, in_cs, cin, w, h, nullptr, 0, r)) {
+            if (unet_conv_tc(ctx, i, in1, cs1, in2, cs2, w, h, nullptr, 0, false, r)) {
                 return 1;
             }
         } else if (L.pool) {
-            if (unet_conv_tc(ctx, i, in, in_cs, cin, w, h, ctx->unet_hs, out_cs, r)) {
+            if (unet_conv_tc(ctx, i, in1, cs1, in2, cs2, w, h, ctx->unet_hs, out_cs, false, r)) {
                 return 1;
             }
-            tc::k_unet_pool_h<<<dim3(w >> 1, h >> 1), 64, 0, s>>>(ctx->unet_hs, out_cs, ctx->unet_ht[i], out_cs, L.cout, w, h);
-        } else if (unet_conv_tc(ctx, i, in, in_cs, cin, w, h, ctx->unet_ht[i], out_cs, r)) {
+            const int c8 = round_up_i(L.cout, 8) / 8;
+            const size_t work = size_t(w >> 1) * size_t(h >> 1) * size_t(c8);
+            tc::k_unet_pool_h<<<unsigned((work + 255) / 256), 256, 0, s>>>(ctx->unet_hs, out_cs, ctx->unet_ht[i], out_cs, c8, w, h);
+        } else if (unet_conv_tc(ctx, i, in1, cs1, in2, cs2, w, h, ctx->unet_ht[i], out_cs, unet_tc_writes_upsampled(i), r)) {
             return 1;
         }
     }
@@ -1601,7 +1614,7 @@ int rc_unet_set_weights(rc_ctx *ctx, const rc_unet_layer layers[16]) {
         CU_CHECK(ctx, cudaMemcpy(ctx->unet_w[i], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU_CHECK(ctx, cudaMemcpy(ctx->unet_b[i], b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
         // tensor-core path: the fp16 bits as they came, [tap][cout padded to 16][input channel stride], zero padded
-        const int n = round_up_i(L.cout, 16), in_cs = round_up_i(unet_tc_cin(i), 64);
+        const int n = round_up_i(L.cout, 16), in_cs = unet_tc_in_cs(i);
         std::vector<uint16_t> hw(size_t(9) * n * in_cs, 0);
         std::vector<float> hb(n, 0.0f);
         for (int co = 0; co < L.cout; ++co) {
