@@ -97,7 +97,7 @@ typedef struct rc_scene_view {
 typedef struct rc_camera {
     uint32_t type;   /* eCamType: only Persp (0) is supported */
     uint32_t filter; /* ePixelFilter */
-    uint32_t view_transform; /* eViewTransform: only Standard (0) */
+    uint32_t view_transform; /* eViewTransform: Standard (0), or 1..9 (AgX / Filmic) after rc_set_view_lut */
     float fov, exposure, gamma, sensor_height;
     float focus_distance, focal_length, fstop, lens_rotation, lens_ratio;
     int32_t lens_blades;
@@ -185,6 +185,12 @@ int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags);
  * what the last rc_upload_scene got and is neither read nor copied.  The node count may differ from the uploaded one
  * (a rebuilt top level rarely has the same size); the instance count may not.  Blocking. */
 int rc_update_instances(rc_ctx *ctx, const rc_scene_view *scene, uint32_t first_tlas_node);
+/* AgX / Filmic view transforms (reference: TonemapFilmic, TonemapRef.cpp:29-66): hands over the 48^3 table of packed
+ * 10-10-10-2 colours for eViewTransform value `view_transform` (1..15; Ray::transform_luts[] in the reference tree --
+ * the tables are reference data and are not part of this library).  lut = NULL drops the table.  rc_render with
+ * cam.view_transform != 0 fails unless its table was set.  The denoisers use the transform of the last rc_render. */
+int rc_set_view_lut(rc_ctx *ctx, uint32_t view_transform, const uint32_t *lut, int dims /* 48 */);
+
 /* Cumulative host->device bytes rc_upload_scene and rc_update_instances have copied on this context. */
 uint64_t rc_scene_upload_bytes(const rc_ctx *ctx);
 

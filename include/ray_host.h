@@ -29,6 +29,8 @@ rh_renderer *rh_create_renderer_multi(int w, int h, const char *devices);
 int rh_device_count(rh_renderer *r);
 /* UNet denoiser (RendererBase::InitUNetFilter + DenoiseImage(pass, region) x pass_count): weights as rc_unet_layer[16] */
 int rh_set_unet_weights(rh_renderer *r, const rc_unet_layer layers[16], uint32_t unet_flags);
+/* AgX / Filmic view transform table (48^3 packed 10-10-10-2) for camera_desc_t::view_transform = view_transform */
+int rh_set_view_lut(rh_renderer *r, uint32_t view_transform, const uint32_t *lut);
 int rh_denoise_unet(rh_renderer *r, const rc_rect *rect, int iteration);
 void rh_destroy_renderer(rh_renderer *r);
 const char *rh_device_name(rh_renderer *r);

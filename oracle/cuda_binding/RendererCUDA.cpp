@@ -28,6 +28,9 @@ extern const uint32_t __pmj02_samples[]; // internal/precomputed/__pmj02_samples
 namespace Cuda {
 // the enumerator a maintainer appends to eRendererType (RendererBase.h:22-34); the unmodified header ends at DirectX12 = 7
 static const eRendererType kTypeCUDA = eRendererType(8);
+} // namespace Cuda
+extern const uint32_t *transform_luts[]; // TonemapRef.cpp:15
+namespace Cuda {
 
 class Scene final : public Cpu::Scene {
     friend class Renderer;
@@ -229,6 +232,12 @@ class Renderer final : public RendererBase {
             throw std::runtime_error("no usable sm_100 CUDA device");
         }
         device_name_ = rc_device_name(ctx_);
+        // AgX / Filmic view transforms: the tree's own tables (TonemapRef.cpp:5-27)
+        for (int vt = 1; vt < int(eViewTransform::_Count); ++vt) {
+            if (rc_set_view_lut(ctx_, uint32_t(vt), transform_luts[vt], 48) != 0) {
+                throw std::runtime_error(rc_last_error(ctx_));
+            }
+        }
         use_tex_compression_ = s.use_tex_compression;
         Resize(s.w, s.h);
     }

@@ -24,14 +24,14 @@
     X(metal_mat2) X(emit_mat0) X(emit_mat1) X(coat_mat0) X(coat_mat1) X(coat_mat2) X(refr_mis0) X(refr_mis1)           \
     X(refr_mis2) X(refr_mat0) X(refr_mat1) X(refr_mat2) X(refr_mat3) X(trans_mat0) X(trans_mat1) X(trans_mat2)         \
     X(trans_mat3) X(trans_mat4) X(trans_mat5)
-// textured (gold-scuffed set, one BC-compressed alpha map, one HDR environment map); no procedural sky / UNet / cache
+// textured (gold-scuffed set, one BC-compressed alpha map, one HDR environment map); complex_mat5_dir_light renders through a Filmic view transform; no procedural sky / cache
 #define COMPLEX5(X)                                                                                                    \
     X(complex_mat5) X(complex_mat5_clipped) X(complex_mat5_adaptive) X(complex_mat5_regions) X(complex_mat5_nlm_filter) \
     X(complex_mat5_dof) X(complex_mat5_mesh_lights) X(complex_mat5_sphere_light) X(complex_mat5_inside_light)          \
-    X(complex_mat5_spot_light) X(complex_mat5_hdri_light) X(two_sided_mat) X(aux_channels)
-// the UNet denoiser (RendererBase::DenoiseImage(pass, region)); complex_mat5_dir_light is parked here too (see below)
-// complex_mat5_dir_light renders through a filmic (LUT) view transform, which this backend does not implement yet
-#define UNET(X) X(ray_flags) X(complex_mat5_unet_filter) X(complex_mat5_dir_light)
+    X(complex_mat5_spot_light) X(complex_mat5_dir_light) X(complex_mat5_hdri_light) X(two_sided_mat) X(aux_channels)       \
+    X(ray_flags)
+// the UNet denoiser (RendererBase::DenoiseImage(pass, region)) through InitUNetFilter with the tree's own weight set
+#define UNET(X) X(complex_mat5_unet_filter)
 UNTEXTURED(T)
 COMPLEX5(T)
 UNET(T)

@@ -38,6 +38,9 @@
 #include "../include/ray_cuda.h"
 #include "../include/ray_scene_desc.h"
 
+namespace Ray {
+extern const uint32_t *transform_luts[]; // TonemapRef.cpp:15
+}
 using namespace Ray;
 
 // the OIDN weight set the reference's UNet filter uses (Apache-2.0 data file of the reference tree, included from where
@@ -963,6 +966,9 @@ int ro_denoise_unet(ro_renderer *r, const rc_rect *rect, int iteration) {
     }
     return props.pass_count;
 }
+
+// the 48^3 packed table of AgX / Filmic view transform `vt` (TonemapRef.cpp:5-27), for rc_set_view_lut in the parity tests
+const uint32_t *ro_view_lut(int vt) { return (vt > 0 && vt < int(Ray::eViewTransform::_Count)) ? Ray::transform_luts[vt] : nullptr; }
 
 // layer i (pass order) of the reference's UNet weight set: fp16 OIHW weights + fp16 biases
 void ro_unet_layer(int i, const uint16_t **weights, int *weights_count, const uint16_t **bias, int *bias_count) {

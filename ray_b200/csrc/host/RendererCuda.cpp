@@ -394,6 +394,16 @@ bool Renderer::SetUNetWeights(const rc_unet_layer layers[16]) {
     return true;
 }
 
+bool Renderer::SetViewTransformLUT(uint32_t view_transform, const uint32_t *lut) {
+    for (rc_ctx *c : ctxs_) {
+        if (rc_set_view_lut(c, view_transform, lut, 48) != 0) {
+            log_->Error("Ray(CUDA): %s", rc_last_error(c));
+            return false;
+        }
+    }
+    return true;
+}
+
 unet_filter_properties_t Renderer::InitUNetFilter(bool, const ParallelFor &) {
     unet_filter_properties_t props = {};
     if (!unet_weights_set_) {

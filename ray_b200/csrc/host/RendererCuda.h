@@ -81,6 +81,9 @@ class Renderer final : public RendererBase {
     void SetRenderFlags(uint32_t rc_render_flags) { render_flags_ = rc_render_flags; }
     /// The 16 convolutions of the UNet denoiser as fp16 OIHW weights + biases (include/ray_cuda.h rc_unet_layer).
     bool SetUNetWeights(const rc_unet_layer layers[16]);
+    // 48^3 packed table of an AgX / Filmic view transform (Ray::transform_luts[view_transform] inside the reference
+    // tree; the stand-alone library does not carry the tables)
+    bool SetViewTransformLUT(uint32_t view_transform, const uint32_t *lut);
     void SetUNetFlags(uint32_t rc_unet_flags) { unet_flags_ = rc_unet_flags; }
     /// Forget the uploaded scene: the next RenderScene copies all scene arrays host->device again (dynamic scenes,
     /// end-to-end measurements).

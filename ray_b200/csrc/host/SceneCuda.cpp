@@ -992,9 +992,7 @@ static void make_camera(const camera_desc_t &c, camera_t &cam, ILog *log) {
     if (c.type != RS_CAM_PERSP) {
         log->Error("Ray(CUDA): only perspective cameras are supported by the CUDA backend");
     }
-    if (c.view_transform != RS_VIEW_STANDARD) {
-        log->Error("Ray(CUDA): only the Standard view transform is supported by the CUDA backend");
-    }
+    // AgX / Filmic view transforms need their table (Cuda::Renderer::SetViewTransformLUT): checked at render time
     float o[3] = {c.origin[0], c.origin[1], c.origin[2]}, f[3] = {c.fwd[0], c.fwd[1], c.fwd[2]},
           u[3] = {c.up[0], c.up[1], c.up[2]};
     if ((0.0f + u[0] * u[0]) + u[1] * u[1] + u[2] * u[2] < 0.0000001f) {

@@ -176,6 +176,9 @@ int rh_set_unet_weights(rh_renderer *r, const rc_unet_layer layers[16], uint32_t
     R(r)->SetUNetFlags(unet_flags);
     return R(r)->SetUNetWeights(layers) ? 0 : 1;
 }
+int rh_set_view_lut(rh_renderer *r, uint32_t view_transform, const uint32_t *lut) {
+    return R(r)->SetViewTransformLUT(view_transform, lut) ? 0 : 1;
+}
 int rh_denoise_unet(rh_renderer *r, const rc_rect *rect, int iteration) {
     const unet_filter_properties_t props = R(r)->InitUNetFilter(false, parallel_for_serial);
     RegionContext region(rect_t{rect->x, rect->y, rect->w, rect->h});

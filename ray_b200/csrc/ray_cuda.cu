@@ -83,7 +83,9 @@ struct rc_ctx {
     void *tensor_map_encode = nullptr; // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint
     float4 *nlm_scratch = nullptr; // 3 planes of the grown region (rt_denoise.cuh)
     size_t nlm_scratch_elems = 0;
-    float last_inv_gamma = 1.0f, last_variance_threshold = 0.0f; // tonemap_params_ / variance_threshold_ of the reference
+    uint32_t *d_view_lut[16] = {}; // AgX / Filmic view-transform tables by eViewTransform (rc_set_view_lut)
+    DisplayXf last_xf{nullptr, 1.0f}; // tonemap_params_ of the reference: what the denoisers' display transform uses
+    float last_variance_threshold = 0.0f; // tonemap_params_ / variance_threshold_ of the reference
     SceneEnv env{};
     float *d_srgb_lut = nullptr;
     bool have_scene = false;
@@ -217,8 +219,8 @@ int fill_params(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
     if (c.type != 0) {
         return fail(ctx, "camera type %u is not supported by the CUDA backend (only Persp)", c.type);
     }
-    if (c.view_transform != 0) {
-        return fail(ctx, "view transform %u is not supported by the CUDA backend (only Standard)", c.view_transform);
+    if (c.view_transform != 0 && (c.view_transform >= 16 || !ctx->d_view_lut[c.view_transform])) {
+        return fail(ctx, "view transform %u needs its table (rc_set_view_lut)", c.view_transform);
     }
     if (c.filter != 0 && !ctx->d_filter_table) {
         return fail(ctx, "pixel filter %u needs a filter table (rc_upload_tables)", c.filter);
@@ -615,8 +617,9 @@ int enqueue_sample(rc_ctx *ctx, const rc_pass_desc *pass, KParams &p) {
                              ? 0.5f * pass->cam.variance_threshold * pass->cam.variance_threshold
                              : 0.0f;
         const int n = p.rect_w * p.rect_h;
-        k_resolve<<<(n + 255) / 256, 256, 0, s>>>(p, exposure_mul, mix_factor, half_mix_factor, is_class_a, inv_gamma, vt);
-        ctx->last_inv_gamma = inv_gamma;
+        const DisplayXf xf{pass->cam.view_transform ? ctx->d_view_lut[pass->cam.view_transform] : nullptr, inv_gamma};
+        k_resolve<<<(n + 255) / 256, 256, 0, s>>>(p, exposure_mul, mix_factor, half_mix_factor, is_class_a, xf, vt);
+        ctx->last_xf = xf;
         ctx->last_variance_threshold = vt;
         ctx->kernel_launches[KF_RESOLVE]++;
         k_accumulate_totals<<<1, 32, 0, s>>>(p, max_bounces);
@@ -835,6 +838,10 @@ void rc_destroy(rc_ctx *ctx) {
     }
     for (auto &e : ctx->user_events) {
         cudaEventDestroy(e);
+    }
+    for (uint32_t *&l : ctx->d_view_lut) {
+        cudaFree(l);
+        l = nullptr;
     }
     cudaFree(ctx->fb.temp);
     cudaFree(ctx->fb.full);
@@ -1205,6 +1212,26 @@ int resize_keep(rc_ctx *ctx, DevArray &a, uint32_t keep, uint32_t new_count) {
 }
 } // namespace
 
+int rc_set_view_lut(rc_ctx *ctx, uint32_t view_transform, const uint32_t *lut, int dims) {
+    if (!ctx || view_transform == 0 || view_transform >= 16 || dims != kViewLutDims) {
+        return fail(ctx, "rc_set_view_lut: view transform %u / table size %d^3 not accepted (1..15, %d^3)", view_transform, dims,
+                    kViewLutDims);
+    }
+    cudaSetDevice(ctx->device);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->last_xf.lut == ctx->d_view_lut[view_transform]) {
+        ctx->last_xf.lut = nullptr;
+    }
+    cudaFree(ctx->d_view_lut[view_transform]);
+    ctx->d_view_lut[view_transform] = nullptr;
+    if (lut) {
+        const size_t bytes = size_t(dims) * dims * dims * sizeof(uint32_t);
+        CU_CHECK(ctx, cudaMalloc(&ctx->d_view_lut[view_transform], bytes));
+        CU_CHECK(ctx, cudaMemcpy(ctx->d_view_lut[view_transform], lut, bytes, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
 uint64_t rc_scene_upload_bytes(const rc_ctx *ctx) { return ctx ? ctx->scene_h2d_bytes : 0; }
 
 int rc_update_instances(rc_ctx *ctx, const rc_scene_view *sv, uint32_t first_node) {
@@ -1523,7 +1550,7 @@ int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in1, int cs1, const __hal
     p.tiles = p.tiles_x * h;
     p.last = (layer == kUNetLayers - 1);
     p.rx = r.x, p.ry = r.y, p.rw = r.w, p.rh = r.h;
-    p.inv_gamma = ctx->last_inv_gamma;
+    p.xf = ctx->last_xf;
     // every CTA asks for the same shared memory whatever the layer: more than a third of an SM's 227 KB, so that at most
     // two CTAs (2 x 2 accumulators of <= 128 columns = the 512 TMEM columns) are ever resident on an SM
     const int smem = tc::kSmemBudget + 1024;
@@ -1695,7 +1722,7 @@ int rc_denoise_unet(rc_ctx *ctx, int pass, const rc_rect *rect, uint32_t flags) 
         p.feat_in1 = in1_of[i] == -2;
         p.feat_in2 = in2_of[i] == -2;
         p.last = (i == kUNetLayers - 1);
-        p.inv_gamma = ctx->last_inv_gamma;
+        p.xf = ctx->last_xf;
         p.in1 = in1_of[i] >= 0 ? ctx->unet_t[in1_of[i]] : nullptr;
         p.in2 = in2_of[i] >= 0 ? ctx->unet_t[in2_of[i]] : nullptr;
         p.weights = ctx->unet_w[i];
@@ -1814,7 +1841,7 @@ int rc_denoise_nlm(rc_ctx *ctx, const rc_rect *rect, int iteration) {
     p.var_f = ctx->nlm_scratch + 2 * plane;
     p.variance_threshold = ctx->last_variance_threshold;
     p.iteration = iteration;
-    p.inv_gamma = ctx->last_inv_gamma;
+    p.xf = ctx->last_xf;
     cudaStream_t s = ctx->stream;
     cudaEvent_t e0 = ctx->user_events[8], e1 = ctx->user_events[9];
     if (e0 && e1) {

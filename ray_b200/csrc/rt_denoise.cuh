@@ -27,7 +27,7 @@ struct NlmParams {
     float4 *temp_final, *var_h, *var_f; // ew * eh scratch planes
     float variance_threshold;
     int iteration;
-    float inv_gamma;
+    DisplayXf xf;
 };
 
 RT_DEV float4 f4_mul(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -179,13 +179,8 @@ __global__ void __launch_bounds__(kNlmBx *kNlmBy) k_nlm_filter(NlmParams p) {
     const float4 col = make_float4(sum_output.x / di, sum_output.y / di, sum_output.z / di, sum_output.w / di);
     const int pix = gy * w + gx;
     p.fb.raw[pix] = col;
-    float4 c = make_float4(tonemap_standard(col.x), tonemap_standard(col.y), tonemap_standard(col.z), col.w);
-    if (p.inv_gamma != 1.0f) {
-        c.x = libm_powf(c.x, p.inv_gamma);
-        c.y = libm_powf(c.y, p.inv_gamma);
-        c.z = libm_powf(c.z, p.inv_gamma);
-        c.w = libm_powf(c.w, 1.0f);
-    }
+    float4 c = col;
+    display_transform(p.xf, c);
     c.x = sse_max(0.0f, sse_min(c.x, 1.0f));
     c.y = sse_max(0.0f, sse_min(c.y, 1.0f));
     c.z = sse_max(0.0f, sse_min(c.z, 1.0f));

@@ -444,8 +444,57 @@ RT_DEV float tonemap_standard(float c) {
     return 1.055f * libm_powf(c, (1.0f / 2.4f)) - 0.055f;
 }
 
+// TonemapFilmic (TonemapRef.cpp:29-66): the AgX / Filmic view transforms are 48^3 tables of packed 10-10-10-2 colours
+// (handed in through rc_set_view_lut -- the tables are the caller's data), sampled with a trilinear fetch
+constexpr int kViewLutDims = 48;
+RT_DEV v3 fetch_view_lut(const uint32_t *__restrict__ lut, int ix, int iy, int iz) {
+    const uint32_t v = lut[(iz * kViewLutDims + iy) * kViewLutDims + ix];
+    return v3{float(int(v & 0x3ffu)) * (1.0f / 1023.0f), float(int((v >> 10) & 0x3ffu)) * (1.0f / 1023.0f),
+              float(int((v >> 20) & 0x3ffu)) * (1.0f / 1023.0f)};
+}
+RT_DEV v3 tonemap_filmic(const uint32_t *__restrict__ lut, v3 color) {
+    const v3 uv = v3{color.x / (color.x + 1.0f) * float(kViewLutDims - 1), color.y / (color.y + 1.0f) * float(kViewLutDims - 1),
+                     color.z / (color.z + 1.0f) * float(kViewLutDims - 1)};
+    // ivec4(uv) truncates; the clamp only guards table reads for non-finite colours (the reference would read out of bounds)
+    const int ix = min(max(int(uv.x), 0), kViewLutDims - 1), iy = min(max(int(uv.y), 0), kViewLutDims - 1),
+              iz = min(max(int(uv.z), 0), kViewLutDims - 1);
+    const float fx = fractf(uv.x), fy = fractf(uv.y), fz = fractf(uv.z);
+    const int jx = min(ix + 1, kViewLutDims - 1), jy = min(iy + 1, kViewLutDims - 1), jz = min(iz + 1, kViewLutDims - 1);
+    const v3 c000 = fetch_view_lut(lut, ix, iy, iz), c001 = fetch_view_lut(lut, jx, iy, iz),
+             c010 = fetch_view_lut(lut, ix, jy, iz), c011 = fetch_view_lut(lut, jx, jy, iz),
+             c100 = fetch_view_lut(lut, ix, iy, jz), c101 = fetch_view_lut(lut, jx, iy, jz),
+             c110 = fetch_view_lut(lut, ix, jy, jz), c111 = fetch_view_lut(lut, jx, jy, jz);
+    const v3 c00x = (1.0f - fx) * c000 + fx * c001, c01x = (1.0f - fx) * c010 + fx * c011,
+             c10x = (1.0f - fx) * c100 + fx * c101, c11x = (1.0f - fx) * c110 + fx * c111;
+    const v3 c0xx = (1.0f - fy) * c00x + fy * c01x, c1xx = (1.0f - fy) * c10x + fy * c11x;
+    return (1.0f - fz) * c0xx + fz * c1xx;
+}
+
+// Tonemap (TonemapRef.h:36-48) without the final saturate: view transform (Standard when lut == nullptr), then 1/gamma
+struct DisplayXf {
+    const uint32_t *lut;
+    float inv_gamma;
+};
+RT_DEV void display_transform(const DisplayXf &xf, float4 &c) {
+    if (xf.lut == nullptr) {
+        c.x = tonemap_standard(c.x);
+        c.y = tonemap_standard(c.y);
+        c.z = tonemap_standard(c.z);
+    } else {
+        const v3 t = tonemap_filmic(xf.lut, v3{c.x, c.y, c.z});
+        c.x = t.x;
+        c.y = t.y;
+        c.z = t.z;
+    }
+    if (xf.inv_gamma != 1.0f) {
+        c.x = libm_powf(c.x, xf.inv_gamma);
+        c.y = libm_powf(c.y, xf.inv_gamma);
+        c.z = libm_powf(c.z, xf.inv_gamma);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_resolve(KParams p, float exposure_mul, float mix_factor, float half_mix_factor,
-                                                 int is_class_a, float inv_gamma, float variance_threshold) {
+                                                 int is_class_a, DisplayXf xf, float variance_threshold) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.rect_w * p.rect_h) {
         return;
@@ -471,13 +520,8 @@ __global__ void __launch_bounds__(256) k_resolve(KParams p, float exposure_mul, 
         }
     }
     p.fb.raw[pix] = full;
-    float4 c = make_float4(tonemap_standard(full.x), tonemap_standard(full.y), tonemap_standard(full.z), full.w);
-    if (inv_gamma != 1.0f) {
-        c.x = libm_powf(c.x, inv_gamma);
-        c.y = libm_powf(c.y, inv_gamma);
-        c.z = libm_powf(c.z, inv_gamma);
-        c.w = libm_powf(c.w, 1.0f);
-    }
+    float4 c = full;
+    display_transform(xf, c);
     // saturate = _mm_max_ps(0, _mm_min_ps(c, 1))
     c.x = sse_max(0.0f, sse_min(c.x, 1.0f));
     c.y = sse_max(0.0f, sse_min(c.y, 1.0f));

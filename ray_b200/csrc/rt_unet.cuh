@@ -113,7 +113,7 @@ struct UNetConvParams {
     int w, h;             // conv grid (rounded frame >> level)
     int rx, ry, rw, rh;   // region of the conv grid to compute
     int up, pool, feat_in2, feat_in1, last;
-    float inv_gamma;
+    DisplayXf xf;
 };
 
 constexpr int kConvTile = 8;      // 8 x 8 output pixels per block
@@ -224,14 +224,7 @@ __global__ void __launch_bounds__(64) k_unet_conv_f32(UNetConvParams p) {
             const float4 full = p.fb.full[pix];
             float4 c = make_float4(unet_tf::output_hdr(acc[0]), unet_tf::output_hdr(acc[1]), unet_tf::output_hdr(acc[2]), full.w);
             p.fb.raw[pix] = c;
-            c.x = tonemap_standard(c.x);
-            c.y = tonemap_standard(c.y);
-            c.z = tonemap_standard(c.z);
-            if (p.inv_gamma != 1.0f) {
-                c.x = libm_powf(c.x, p.inv_gamma);
-                c.y = libm_powf(c.y, p.inv_gamma);
-                c.z = libm_powf(c.z, p.inv_gamma);
-            }
+            display_transform(p.xf, c);
             c.x = sse_max(0.0f, sse_min(c.x, 1.0f));
             c.y = sse_max(0.0f, sse_min(c.y, 1.0f));
             c.z = sse_max(0.0f, sse_min(c.z, 1.0f));

@@ -102,7 +102,7 @@ struct ConvTcParams {
     int tiles_x, tiles;  // row segments per image row, total
     int last;
     int rx, ry, rw, rh;  // last layer: frame rect whose pixels are written
-    float inv_gamma;
+    DisplayXf xf;
 };
 
 // Persistent CTAs: tile t = blockIdx.x + k gridDim.x.  The TMA producer runs ahead across tile boundaries; the MMA issuer
@@ -265,14 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_unet_conv_tc(const __grid_constant
                 const float4 full = p.fb.full[pix];
                 float4 c = make_float4(unet_tf::output_hdr(outv[0]), unet_tf::output_hdr(outv[1]), unet_tf::output_hdr(outv[2]), full.w);
                 p.fb.raw[pix] = c;
-                c.x = tonemap_standard(c.x);
-                c.y = tonemap_standard(c.y);
-                c.z = tonemap_standard(c.z);
-                if (p.inv_gamma != 1.0f) {
-                    c.x = libm_powf(c.x, p.inv_gamma);
-                    c.y = libm_powf(c.y, p.inv_gamma);
-                    c.z = libm_powf(c.z, p.inv_gamma);
-                }
+                display_transform(p.xf, c);
                 c.x = sse_max(0.0f, sse_min(c.x, 1.0f));
                 c.y = sse_max(0.0f, sse_min(c.y, 1.0f));
                 c.z = sse_max(0.0f, sse_min(c.z, 1.0f));

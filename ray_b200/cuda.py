@@ -71,6 +71,7 @@ def load_library():
         "rc_build_lbvh": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
         "rc_update_instances": (C.c_int, [vp, vp, C.c_uint32]),
         "rc_scene_upload_bytes": (C.c_uint64, [vp]),
+        "rc_set_view_lut": (C.c_int, [vp, C.c_uint32, vp, C.c_int]),
         "rc_denoise_unet": (C.c_int, [vp, C.c_int, P(capi.rc_rect), C.c_uint32]),
         "rc_comm_init": (C.c_int, [P(vp), C.c_int, P(vp)]),
         "rc_comm_destroy": (None, [vp]),
@@ -100,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "rc_stage_sort_rays", "rc_debug_fill_temp", "rc_abi_sizeof", "rc_host_alloc", "rc_host_free", "rc_device_ptr",
     "rc_event_record", "rc_event_elapsed_ms", "rc_readback_async", "rc_comm_init", "rc_comm_destroy", "rc_comm_last_error",
     "rc_comm_strip", "rc_comm_upload_scene", "rc_comm_upload_tables", "rc_comm_render", "rc_comm_sync", "rc_gather",
-    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet", "rc_build_lbvh", "rc_update_instances", "rc_scene_upload_bytes",
+    "rc_gather_device", "rc_comm_get_counters", "rc_unet_set_weights", "rc_denoise_unet", "rc_build_lbvh", "rc_update_instances", "rc_scene_upload_bytes", "rc_set_view_lut",
 ]
 
 
@@ -162,6 +163,15 @@ class Context:
 
     def update_instances(self, view: capi.rc_scene_view, first_tlas_node):
         self._check(self.lib.rc_update_instances(self._ctx, C.byref(view), first_tlas_node), "rc_update_instances")
+
+    def set_view_lut(self, view_transform, lut):
+        """lut: 48^3 uint32 (packed 10-10-10-2) or None"""
+        if lut is None:
+            self._check(self.lib.rc_set_view_lut(self._ctx, view_transform, None, 48), "rc_set_view_lut")
+            return
+        lut = np.ascontiguousarray(lut, dtype=np.uint32)
+        assert lut.size == 48 ** 3
+        self._check(self.lib.rc_set_view_lut(self._ctx, view_transform, lut.ctypes.data, 48), "rc_set_view_lut")
 
     def scene_upload_bytes(self):
         return int(self.lib.rc_scene_upload_bytes(self._ctx))

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libray_host.so")
 FINAL, RAW, BASE_COLOR, DEPTH_NORMALS = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
-    "rh_create_renderer", "rh_create_renderer_multi", "rh_device_count", "rh_set_unet_weights", "rh_denoise_unet", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
+    "rh_create_renderer", "rh_create_renderer_multi", "rh_device_count", "rh_set_unet_weights", "rh_set_view_lut", "rh_denoise_unet", "rh_destroy_renderer", "rh_device_name", "rh_error_count", "rh_last_error", "rh_resize",
     "rh_clear", "rh_create_scene", "rh_destroy_scene", "rh_set_environment", "rh_denoise", "rh_add_texture", "rh_add_material_node",
     "rh_add_material_principled", "rh_add_mesh", "rh_add_mesh_instance", "rh_set_mesh_instance_transform",
     "rh_remove_mesh_instance", "rh_add_light_directional",
@@ -49,6 +49,7 @@ def load_library():
         "rh_create_renderer_multi": (vp, [C.c_int, C.c_int, C.c_char_p]),
         "rh_device_count": (C.c_int, [vp]),
         "rh_set_unet_weights": (C.c_int, [vp, vp, C.c_uint32]),
+        "rh_set_view_lut": (C.c_int, [vp, C.c_uint32, vp]),
         "rh_denoise_unet": (C.c_int, [vp, P(capi.rc_rect), C.c_int]),
         "rh_destroy_renderer": (None, [vp]),
         "rh_device_name": (C.c_char_p, [vp]),
@@ -287,6 +288,12 @@ class Renderer:
             arr[i] = L(w.ctypes.data, b.ctypes.data, w.shape[1], w.shape[0])
         if self.lib.rh_set_unet_weights(self.h, C.byref(arr), flags) != 0:
             self.check()
+
+    def set_view_lut(self, view_transform, lut):
+        lut = np.ascontiguousarray(lut, dtype=np.uint32)
+        assert lut.size == 48 ** 3
+        if self.lib.rh_set_view_lut(self.h, view_transform, lut.ctypes.data) != 0:
+            raise HostError(self.lib.rh_last_error(self.h).decode())
 
     def denoise_unet(self, rect, iteration):
         r = capi.rc_rect(*rect)

@@ -61,6 +61,7 @@ def load():
         "ro_render": (None, [vp, vp, P(capi.rc_rect), P(C.c_int)]),
         "ro_denoise": (None, [vp, P(capi.rc_rect), C.c_int]),
         "ro_denoise_unet": (C.c_int, [vp, P(capi.rc_rect), C.c_int]),
+        "ro_view_lut": (P(C.c_uint32), [C.c_int]),
         "ro_unet_layer": (None, [C.c_int, P(P(C.c_uint16)), P(C.c_int), P(P(C.c_uint16)), P(C.c_int)]),
         "ro_get_pixels": (P(C.c_float), [vp, C.c_int, P(C.c_int)]),
         "ro_get_stats": (None, [vp, P(C.c_uint64)]),
@@ -84,6 +85,13 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def view_lut(view_transform):
+    """The reference's 48^3 packed table of an AgX / Filmic view transform (for rc_set_view_lut)."""
+    ptr = load().ro_view_lut(int(view_transform))
+    assert ptr, view_transform
+    return np.ctypeslib.as_array(ptr, shape=(48 ** 3,)).copy()
 
 
 def unet_layers():

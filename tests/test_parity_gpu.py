@@ -233,6 +233,40 @@ def test_nlm_denoise_matches_reference_renderer(oracle_mod):
     pair.close()
 
 
+@pytest.mark.parametrize("view_transform", [1, 2, 6, 9])  # AgX, AgX_Punchy, Filmic_MediumContrast, Filmic_VeryHighContrast
+def test_lut_view_transforms_match_reference_renderer(oracle_mod, view_transform):
+    """camera_desc_t::view_transform = AgX / Filmic (TonemapFilmic, TonemapRef.cpp:29-66): the 48^3 table comes from the
+    reference through rc_set_view_lut; the tonemapped plane after rc_render and after the NLM denoiser is bit-identical,
+    with a non-unit gamma on top.  Without the table the render call fails loudly."""
+    desc = scenes.cornell_box(80, 64)
+    desc.camera.view_transform = view_transform
+    desc.camera.gamma = 1.8
+    desc.camera.exposure = 0.5
+    pair = Pair(oracle_mod, desc)
+    assert pair.cam.view_transform == view_transform
+    with pytest.raises(Exception):
+        pair.ctx.render(pair.make_pass(1))
+    pair.ctx.set_view_lut(view_transform, oracle_mod.view_lut(view_transform))
+    spp = 6
+    ref = oracle_mod.Renderer(capi.RT_REFERENCE, pair.w, pair.h)
+    it = 0
+    for _ in range(spp):
+        it = ref.render(pair.osc, (0, 0, pair.w, pair.h), it)
+    pair.ctx.clear((0, 0, 0, 0))
+    for i in range(1, spp + 1):
+        pair.ctx.render(pair.make_pass(i))
+    assert bits_equal(pair.ctx.readback(capi.RC_BUF_RAW), ref.pixels(1))
+    final, ref_final = pair.ctx.readback(capi.RC_BUF_FINAL), ref.pixels(0)
+    assert bits_equal(final, ref_final), f"tonemapped plane: L-inf {np.abs(final - ref_final).max()}"
+    assert final[..., :3].std() > 0.01
+    rect = (0, 0, pair.w, pair.h)
+    ref.denoise(rect, it)
+    pair.ctx.denoise_nlm(rect, it)
+    assert bits_equal(pair.ctx.readback(capi.RC_BUF_FINAL), ref.pixels(0))
+    ref.close()
+    pair.close()
+
+
 def test_unet_denoise_matches_reference_renderer(oracle_mod):
     """RendererBase::DenoiseImage(pass, region) (SURVEY 8(f)-3, UNet half): same 8 spp accumulated on both sides
     (bit-identical), then the 16-pass UNet with the reference's own weight set handed over through rc_unet_set_weights.

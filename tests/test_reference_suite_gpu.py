@@ -4,9 +4,10 @@ INTEGRATION.md compiled for real (oracle/cuda_binding/RendererCUDA.cpp: Ray::Cud
 Ray::Cuda::Scene : Cpu::Scene).  Every case must pass the reference's own gates (PSNR against the committed ref.tga,
 firefly count) and must not raise a single ILog::Error -- the bar `test_Ray --arch <any backend>` holds every backend to.
 
-Cases: the 51 untextured material cases and 13 textured ones (complex_mat5 and its light / DOF / clipping / adaptive /
-region / NLM / HDR-environment variants, two_sided_mat with a BC-compressed alpha map, aux_channels) -- everything that
-needs neither the procedural sky, the UNet filter nor the spatial cache."""
+Cases: the 51 untextured material cases, 15 textured ones (complex_mat5 and its light / DOF / clipping / adaptive /
+region / NLM / HDR-environment variants, the sun light through a Filmic view transform, two_sided_mat with a
+BC-compressed alpha map, aux_channels, ray_flags) and the UNet-filtered complex_mat5 -- everything that needs neither the
+procedural sky nor the spatial cache."""
 import os
 import re
 import subprocess
@@ -20,7 +21,7 @@ CWD = os.path.join(ROOT, "oracle", "_ref", "test_run")
 pytestmark = [pytest.mark.gpu, pytest.mark.slow]
 
 
-@pytest.mark.parametrize("group,expected", [("untextured", 51), ("complex5", 13)])
+@pytest.mark.parametrize("group,expected", [("untextured", 51), ("complex5", 15), ("unet", 1)])
 def test_reference_regression_suite_passes_on_the_cuda_backend(group, expected):
     if not (os.path.exists(BIN) and os.path.isdir(os.path.join(CWD, "test_data"))):
         pytest.skip("oracle/_ref/test_ray_cuda not built (make -C oracle ref_tests; needs /root/reference)")
