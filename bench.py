@@ -510,6 +510,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "scene_bytes_uploaded_once": int(scene_bytes),
                     "scene_upload_plus_one_step_ms": upload_plus_step_ms,
                     "pinned_shared_frame": (shared.pinned if shared else True),
+                    "one_shared_host_frame": (bool(getattr(shared, "shared", True)) if shared else True),
                     "note": "per step: one blocking RenderScene (pass descriptor host->device) + the whole frame "
                             "device->host into page-locked memory (1 GPU: the renderer's mirror, as get_raw_pixels_ref; "
                             "N GPUs: every rank copies its strip into one shared host frame, then a barrier); the "

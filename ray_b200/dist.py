@@ -92,21 +92,38 @@ class SharedHostFrame:
         self.nbytes = w * h * 16
         rank = dist.get_rank() if dist.is_initialized() else 0
         self.rank = rank
+        self.shm = None
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
-            name = [self.shm.name]
+            # tmpfs allocates on first touch: a block larger than what /dev/shm has left would be created fine and
+            # kill the writers with SIGBUS later, so check the space first and tell every rank when sharing is off
+            try:
+                import os
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < self.nbytes + (64 << 20):
+                    raise OSError("/dev/shm has %d MB free, the frame needs %d MB" % (st.f_bavail * st.f_frsize >> 20, self.nbytes >> 20))
+                self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+                name = [self.shm.name]
+            except Exception as e:  # noqa: BLE001
+                self.why_not_shared = str(e)
+                name = [""]
         else:
             name = [None]
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.broadcast_object_list(name, src=0)
-        if rank != 0:
+        self.shared = bool(name[0])
+        if rank != 0 and self.shared:
             self.shm = shared_memory.SharedMemory(name=name[0])
             try:  # rank 0 owns the block: keep this process's resource tracker from unlinking / warning about it
                 from multiprocessing import resource_tracker
                 resource_tracker.unregister(self.shm._name, "shared_memory")
             except Exception:
                 pass
-        self.array = np.ndarray((h, w, 4), dtype=np.float32, buffer=self.shm.buf)
+        if not self.shared:
+            # no shared block: every rank keeps a private page-locked frame and fills only its own strip -- the same N
+            # parallel device->host copies, but the strips do not land in one address space
+            self.array = np.zeros((h, w, 4), dtype=np.float32)
+        else:
+            self.array = np.ndarray((h, w, 4), dtype=np.float32, buffer=self.shm.buf)
         self.pinned = False
         if pin:
             try:
@@ -135,9 +152,10 @@ class SharedHostFrame:
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.barrier()
         try:
-            self.shm.close()
-            if self.rank == 0:
-                self.shm.unlink()
+            if self.shm is not None:
+                self.shm.close()
+                if self.rank == 0:
+                    self.shm.unlink()
         except Exception:
             pass
 
