@@ -1524,8 +1524,8 @@ int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in1, int cs1, const __hal
     const int n = round_up_i(L.cout, 16);
     const size_t rows = size_t(w + 2) * size_t(h + 2);
     CUtensorMap map_a1, map_a2, map_b;
-    if (make_map(ctx, &map_a1, in1, cs1, rows, tc::kTileM) ||
-        make_map(ctx, &map_a2, in2 ? in2 : in1, in2 ? cs2 : cs1, rows, tc::kTileM) ||
+    if (make_map(ctx, &map_a1, in1, cs1, rows, tc::kHaloRows) ||
+        make_map(ctx, &map_a2, in2 ? in2 : in1, in2 ? cs2 : cs1, rows, tc::kHaloRows) ||
         make_map(ctx, &map_b, ctx->unet_hw[layer], unet_tc_in_cs(layer), size_t(9) * n, n)) {
         return 1;
     }
@@ -1544,16 +1544,28 @@ int unet_conv_tc(rc_ctx *ctx, int layer, const __half *in1, int cs1, const __hal
     p.out_cs = out_cs;
     p.up = up ? 1 : 0;
     p.tmem_cols = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
-    const int stage_bytes = tc::kATileBytes + ((n * tc::kBlockK * 2 + 1023) & ~1023);
-    p.stages = std::min(tc::kMaxStages, tc::kSmemBudget / stage_bytes);
+    const int b_slot_bytes = (n * tc::kBlockK * 2 + 1023) & ~1023;
+    const int nkb = p.nkb1 + p.nkb2;
+    p.base_offset = 0; // measured: the swizzle is a function of the absolute shared address, a shifted start needs no base offset
     p.tiles_x = (w + tc::kTileM - 1) / tc::kTileM;
     p.tiles = p.tiles_x * h;
     p.last = (layer == kUNetLayers - 1);
     p.rx = r.x, p.ry = r.y, p.rw = r.w, p.rh = r.h;
     p.xf = ctx->last_xf;
-    // every CTA asks for the same shared memory whatever the layer: more than a third of an SM's 227 KB, so that at most
-    // two CTAs (2 x 2 accumulators of <= 128 columns = the 512 TMEM columns) are ever resident on an SM
+    // Shared memory plan.  Every CTA asks for more than a third of an SM's 227 KB whatever the layer, so that at most two
+    // CTAs (2 x 2 accumulators of <= 128 columns = the 512 TMEM columns) are ever resident on an SM.  A filter that fits
+    // next to a >= 3-slot activation ring stays resident; otherwise the weights stream through a B ring.
+    const int b_all_bytes = 9 * nkb * b_slot_bytes;
     const int smem = tc::kSmemBudget + 1024;
+    if (b_all_bytes + 3 * tc::kASlotBytes <= tc::kSmemBudget) {
+        p.b_resident = 1;
+        p.a_slots = std::min(tc::kMaxASlots, (tc::kSmemBudget - b_all_bytes) / tc::kASlotBytes);
+        p.stages = 1;
+    } else {
+        p.b_resident = 0;
+        p.a_slots = 3;
+        p.stages = std::min(tc::kMaxStages, (tc::kSmemBudget - p.a_slots * tc::kASlotBytes) / b_slot_bytes);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(tc::k_unet_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

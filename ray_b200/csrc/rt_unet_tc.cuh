@@ -19,7 +19,13 @@
 // grid (nearest up-sampling fused into its epilogue).  Epilogue: tcgen05.ld -> bias + ReLU -> fp16 -> NHWC store (or,
 // for the last layer, inverse HDR transfer + display transform into the RAW / FINAL planes).
 // CTAs are persistent (2 per SM), each with two TMEM accumulators: the epilogue of one tile overlaps the TMA loads and
-// MMAs of the next.  1080p, all 16 layers: 2.4 ms (4.7 ms with one CTA per tile and separate gather passes; 31 ms fp32).
+// MMAs of the next.  Per image row of the 3 x 3 window ONE haloed activation box (130 pixels) is loaded and multiplied
+// three times, shifted by one pixel per horizontal tap (the 128-byte swizzle is a function of the absolute shared
+// address, so a shifted start address is all the descriptor needs), and a layer whose whole filter fits next to the
+// activation ring keeps it resident for the CTA's lifetime.  1080p, all 16 layers: 2.1 ms (first build, one CTA per tile
+// and separate gather passes: 4.7 ms; fp32 path: 31 ms).  Measured and not kept: weights resident with ONE CTA per SM
+// for the 147 KB filter of dec_conv1a (fewer bytes in flight per SM: slower), L2 tensor prefetch one tile ahead (no gain:
+// the loads are bound by L2 -> SMEM throughput, ~11 TB/s, not by DRAM latency).
 #pragma once
 
 #include <cuda.h>
@@ -30,7 +36,10 @@
 namespace rt {
 namespace tc {
 
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;            // B ring slots (one tap of one K block each)
+constexpr int kMaxASlots = 6;            // A ring slots (one haloed row segment of one K block each)
+constexpr int kHaloRows = 130;           // 128 output pixels + one neighbour each side: serves the three horizontal taps
+constexpr int kASlotBytes = 17 * 1024;   // 130 rows x 128 B, rounded up to the 1024-byte swizzle period
 constexpr int kTileM = 128;              // output pixels per tile (one row segment)
 constexpr int kBlockK = 64;              // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int kThreads = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
@@ -78,10 +87,16 @@ RT_DEV void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t i
                  : "memory");
 }
 // K-major operand tile, rows of 128 bytes, 128-byte swizzle, 8-row groups 1024 bytes apart (cute/arch/mma_sm100_desc.hpp)
-RT_DEV uint64_t umma_desc_sw128(const void *smem_tile) {
-    const uint64_t addr = uint64_t(smem_u32(smem_tile));
+// `row_shift` (0..7): the tile starts that many 128-byte rows past a 1024-byte boundary of the swizzle pattern (the haloed
+// A tile is read three times, shifted by one pixel row per horizontal tap).  Measured on B200: the unit applies the
+// 128-byte swizzle to the ABSOLUTE shared-memory address, so moving the start address is all it takes -- with the
+// descriptor's base-offset field set to the shift the results are wrong, with 0 they are right (use_base_offset stays as
+// the switch that experiment used)
+RT_DEV uint64_t umma_desc_sw128(const void *smem_tile, uint32_t row_shift = 0, uint32_t use_base_offset = 0) {
+    const uint64_t addr = uint64_t(smem_u32(smem_tile)) + row_shift * 128u;
     return ((addr >> 4) & 0x3fffull) | (1ull << 16) /* LBO (ignored for swizzled K-major) */ |
-           (uint64_t(1024 >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version of sm_100 */ | (2ull << 61) /* SWIZZLE_128B */;
+           (uint64_t(1024 >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version of sm_100 */ |
+           (uint64_t(use_base_offset ? (row_shift & 7u) : 0u) << 49) /* matrix base offset */ | (2ull << 61) /* SWIZZLE_128B */;
 }
 // kind::f16 instruction descriptor: D = fp32, A = B = fp16, both K-major, M = 128, N
 RT_DEV uint32_t umma_idesc_f16(int n) { return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileM >> 4) << 24); }
@@ -98,7 +113,10 @@ struct ConvTcParams {
     int out_cs;
     int up;              // write every output pixel to the 2 x 2 block of a (2w x 2h) tensor: nearest up-sampling fused
     int tmem_cols;       // power of two >= max(32, n); the CTA allocates two accumulators
-    int stages;          // pipeline depth that fits kSmemBudget
+    int stages;          // B ring depth that fits kSmemBudget next to the A ring
+    int base_offset;     // descriptor base-offset field carries the row shift (experiment switch, 1 = on)
+    int b_resident;      // the layer's whole weight tensor (9 taps x K blocks) stays in shared memory for the CTA's lifetime
+    int a_slots;         // A ring depth
     int tiles_x, tiles;  // row segments per image row, total
     int last;
     int rx, ry, rw, rh;  // last layer: frame rect whose pixels are written
@@ -114,19 +132,25 @@ __global__ void __launch_bounds__(kThreads) k_unet_conv_tc(const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the 128-byte swizzle pattern repeats every 1024 bytes of SHARED address: align the stage buffers in that space
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_full[2], acc_empty[2];
+    __shared__ uint64_t a_full[kMaxASlots], a_empty[kMaxASlots], b_full[kMaxStages], b_empty[kMaxStages], b_all, acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_tile_bytes = p.n * kBlockK * 2;
-    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) & ~1023);
+    const int b_slot_bytes = (b_tile_bytes + 1023) & ~1023;
+    const int AS = p.a_slots;
+    uint8_t *smem_a = smem, *smem_b = smem + AS * kASlotBytes;
     const int nkb = p.nkb1 + p.nkb2;
-    const int steps = 9 * nkb;
     const int S = p.stages;
 
     if (threadIdx.x == 0) {
+        for (int s = 0; s < AS; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        mbar_init(&b_all, 1);
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -144,28 +168,46 @@ __global__ void __launch_bounds__(kThreads) k_unet_conv_tc(const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
+    // K loop of one tile: for every image row dy of the 3 x 3 window and every 64-channel block ONE haloed A box
+    // (130 pixels) is loaded and multiplied three times, shifted by one pixel per horizontal tap, against the three
+    // B boxes of that row of the filter -- the activations cross L2 -> SMEM 3 times per layer instead of 9
     if (warp == 0) {
         if (lane == 0) {
             // ---- TMA producer ----
-            uint32_t it = 0;
+            uint32_t ia = 0, ib = 0;
+            if (p.b_resident) {
+                // the whole filter (9 taps x K blocks) once; the tile loop then streams activations only
+                mbar_expect_tx(&b_all, uint32_t(9 * nkb * b_tile_bytes));
+                for (int tap = 0; tap < 9; ++tap) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        tma_load_2d(smem_b + (tap * nkb + kb) * b_slot_bytes, &map_b, &b_all, kb * kBlockK, tap * p.n);
+                    }
+                }
+            }
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int y = tile / p.tiles_x, x0 = (tile % p.tiles_x) * kTileM;
-                for (int s = 0; s < steps; ++s, ++it) {
-                    const uint32_t stage = it % uint32_t(S), round = it / uint32_t(S);
-                    if (round > 0) {
-                        mbar_wait(&empty_bar[stage], (round - 1) & 1);
+                for (int dy = 0; dy < 3; ++dy) {
+                    for (int kb = 0; kb < nkb; ++kb, ++ia) {
+                        const uint32_t aslot = ia % uint32_t(AS), around = ia / uint32_t(AS);
+                        if (around > 0) {
+                            mbar_wait(&a_empty[aslot], (around - 1) & 1);
+                        }
+                        mbar_expect_tx(&a_full[aslot], uint32_t(kHaloRows * kBlockK * 2));
+                        const int pix = (y + dy) * (p.w + 2) + x0;
+                        if (kb < p.nkb1) {
+                            tma_load_2d(smem_a + aslot * kASlotBytes, &map_a1, &a_full[aslot], kb * kBlockK, pix);
+                        } else {
+                            tma_load_2d(smem_a + aslot * kASlotBytes, &map_a2, &a_full[aslot], (kb - p.nkb1) * kBlockK, pix);
+                        }
+                        for (int dx = 0; dx < 3 && !p.b_resident; ++dx, ++ib) {
+                            const uint32_t bslot = ib % uint32_t(S), bround = ib / uint32_t(S);
+                            if (bround > 0) {
+                                mbar_wait(&b_empty[bslot], (bround - 1) & 1);
+                            }
+                            mbar_expect_tx(&b_full[bslot], uint32_t(b_tile_bytes));
+                            tma_load_2d(smem_b + bslot * b_slot_bytes, &map_b, &b_full[bslot], kb * kBlockK, (dy * 3 + dx) * p.n);
+                        }
                     }
-                    const int tap = s / nkb, kb = s % nkb;
-                    const int dy = tap / 3, dx = tap % 3;
-                    uint8_t *a = smem + size_t(stage) * stage_bytes, *b = a + kATileBytes;
-                    mbar_expect_tx(&full_bar[stage], uint32_t(kATileBytes + b_tile_bytes));
-                    const int pix = (y + dy) * (p.w + 2) + x0 + dx;
-                    if (kb < p.nkb1) {
-                        tma_load_2d(a, &map_a1, &full_bar[stage], kb * kBlockK, pix);
-                    } else {
-                        tma_load_2d(a, &map_a2, &full_bar[stage], (kb - p.nkb1) * kBlockK, pix);
-                    }
-                    tma_load_2d(b, &map_b, &full_bar[stage], kb * kBlockK, tap * p.n);
                 }
             }
         }
@@ -173,7 +215,10 @@ __global__ void __launch_bounds__(kThreads) k_unet_conv_tc(const __grid_constant
         if (lane == 0) {
             // ---- MMA issuer ----
             const uint32_t idesc = umma_idesc_f16(p.n);
-            uint32_t it = 0, k = 0;
+            uint32_t ia = 0, ib = 0, k = 0;
+            if (p.b_resident) {
+                mbar_wait(&b_all, 0);
+            }
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++k) {
                 const uint32_t buf = k & 1u;
                 if (k >= 2) {
@@ -181,19 +226,38 @@ __global__ void __launch_bounds__(kThreads) k_unet_conv_tc(const __grid_constant
                     tcgen05_fence_after();
                 }
                 const uint32_t tmem_d = tmem_base + buf * uint32_t(p.tmem_cols);
-                for (int s = 0; s < steps; ++s, ++it) {
-                    const uint32_t stage = it % uint32_t(S), round = it / uint32_t(S);
-                    mbar_wait(&full_bar[stage], round & 1);
-                    tcgen05_fence_after();
-                    const int kb = s % nkb;
-                    const int kcount = (kb < p.nkb1 ? min(kBlockK, p.cin1 - kb * kBlockK) : min(kBlockK, p.cin2 - (kb - p.nkb1) * kBlockK)) / 16;
-                    const uint8_t *a = smem + size_t(stage) * stage_bytes, *b = a + kATileBytes;
-                    const uint64_t adesc = umma_desc_sw128(a), bdesc = umma_desc_sw128(b);
-                    for (int kk = 0; kk < kcount; ++kk) {
-                        // 16 fp16 = 32 bytes further along the swizzled 128-byte row: start-address field += 2
-                        umma_f16(tmem_d, adesc + uint64_t(2 * kk), bdesc + uint64_t(2 * kk), idesc, (s > 0 || kk > 0) ? 1u : 0u);
+                uint32_t accumulate = 0;
+                for (int dy = 0; dy < 3; ++dy) {
+                    for (int kb = 0; kb < nkb; ++kb, ++ia) {
+                        const uint32_t aslot = ia % uint32_t(AS), around = ia / uint32_t(AS);
+                        mbar_wait(&a_full[aslot], around & 1);
+                        tcgen05_fence_after();
+                        const int kcount =
+                            (kb < p.nkb1 ? min(kBlockK, p.cin1 - kb * kBlockK) : min(kBlockK, p.cin2 - (kb - p.nkb1) * kBlockK)) / 16;
+                        const uint8_t *a = smem_a + aslot * kASlotBytes;
+                        for (int dx = 0; dx < 3; ++dx) {
+                            uint32_t bslot;
+                            if (p.b_resident) {
+                                bslot = uint32_t((dy * 3 + dx) * nkb + kb);
+                            } else {
+                                bslot = ib % uint32_t(S);
+                                mbar_wait(&b_full[bslot], (ib / uint32_t(S)) & 1);
+                                tcgen05_fence_after();
+                                ++ib;
+                            }
+                            const uint64_t adesc = umma_desc_sw128(a, uint32_t(dx), uint32_t(p.base_offset));
+                            const uint64_t bdesc = umma_desc_sw128(smem_b + bslot * b_slot_bytes);
+                            for (int kk = 0; kk < kcount; ++kk) {
+                                // 16 fp16 = 32 bytes further along the swizzled 128-byte row: start-address field += 2
+                                umma_f16(tmem_d, adesc + uint64_t(2 * kk), bdesc + uint64_t(2 * kk), idesc, accumulate);
+                                accumulate = 1;
+                            }
+                            if (!p.b_resident) {
+                                umma_commit(&b_empty[bslot]); // frees the B slot once these MMAs have read it
+                            }
+                        }
+                        umma_commit(&a_empty[aslot]); // all three taps have read the haloed A box
                     }
-                    umma_commit(&empty_bar[stage]); // frees the stage once these MMAs have read it
                 }
                 umma_commit(&acc_full[buf]); // accumulator complete
             }

@@ -17,7 +17,10 @@ shape = [(9, 32, 0), (32, 32, 0), (32, 48, 1), (48, 64, 2), (64, 80, 3), (80, 96
          (160, 96, 2), (96, 96, 2), (128, 64, 1), (64, 64, 1), (73, 64, 0), (64, 32, 0), (32, 3, 0)]
 flops = sum(2.0 * 9 * ci * co * (wr >> lv) * (hr >> lv) for ci, co, lv in shape)
 out = {}
-for name, flag in (("fp32", capi.RC_UNET_FP32), ("tensor_cores", capi.RC_UNET_TENSOR_CORES)):
+paths = (("fp32", capi.RC_UNET_FP32), ("tensor_cores", capi.RC_UNET_TENSOR_CORES))
+if os.environ.get("TC_ONLY"):
+    paths = paths[1:]
+for name, flag in paths:
     r.set_unet_weights(layers, flag)
     r.denoise_unet((0, 0, w, h), it)  # warm-up (allocations, tensor maps)
     n = 5
