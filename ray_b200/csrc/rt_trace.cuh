@@ -50,11 +50,6 @@ RT_DEV f2 pk2(float lo, float hi) {
 }
 RT_DEV void upk2(f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 RT_DEV f2 bc2(float v) { return pk2(v, v); }
-RT_DEV f2 add2(f2 a, f2 b) {
-    f2 c;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
-    return c;
-}
 RT_DEV f2 sub2(f2 a, f2 b) {
     f2 c;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
@@ -243,142 +238,6 @@ RT_DEV uint32_t box8_near_far(const char *__restrict__ node, AxisSel s, v3 o, v3
     return mask;
 }
 
-// 8-wide plane-form triangle test, reference IntersectTri(mtri_accel_t) CoreRef.cpp:54-119, with the reference's lane
-// semantics (lane k tests triangle k, then k + 4 against the lane's running t; the lowest lane holding the minimum
-// wins).  Same operations in the same order as intersect_mtri (rt_traverse.cuh).  The multiplications go two lanes per
-// instruction (FMUL2); the additions stay scalar: ptxas contracts a packed multiply feeding a packed add into FFMA2
-// even for mul.rn / add.rn.f32x2 and with --fmad=false (CUDA 12.9), which would change the rounding.
-RT_DEV void intersect_mtri_p(const MTri *__restrict__ tri, v3 ro, v3 rd, int prim_base, Hit &inter) {
-    float lt[4], lu[4], lv[4];
-    int lp[4];
-    bool any_lane[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        lt[k] = inter.t;
-        lu[k] = 0.0f;
-        lv[k] = 0.0f;
-        lp[k] = 0;
-        any_lane[k] = false;
-    }
-    const f2 rdx = bc2(rd.x), rdy = bc2(rd.y), rdz = bc2(rd.z);
-    const f2 rox = bc2(ro.x), roy = bc2(ro.y), roz = bc2(ro.z);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const float4 *np = reinterpret_cast<const float4 *>(&tri->n_plane[0][0]) + half;
-        const float4 *up = reinterpret_cast<const float4 *>(&tri->u_plane[0][0]) + half;
-        const float4 *vp = reinterpret_cast<const float4 *>(&tri->v_plane[0][0]) + half;
-        const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 2), n2 = __ldg(np + 4), n3 = __ldg(np + 6);
-        const float nw[4] = {n3.x, n3.y, n3.z, n3.w};
-        float det[4], dett[4];
-        bool act[4];
-        bool any = false;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const f2 nx = q ? pk2(n0.z, n0.w) : pk2(n0.x, n0.y), ny = q ? pk2(n1.z, n1.w) : pk2(n1.x, n1.y);
-            const f2 nz = q ? pk2(n2.z, n2.w) : pk2(n2.x, n2.y);
-            float a[2], b[2], c[2], e[2], f[2], g[2], s[2];
-            upk2(mul2(rdx, nx), a[0], a[1]);
-            upk2(mul2(rdy, ny), b[0], b[1]);
-            upk2(mul2(rdz, nz), c[0], c[1]);
-            upk2(mul2(rox, nx), e[0], e[1]);
-            upk2(mul2(roy, ny), f[0], f[1]);
-            upk2(mul2(roz, nz), g[0], g[1]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int k = 2 * q + j;
-                det[k] = a[j] + b[j] + c[j];
-                dett[k] = nw[k] - e[j] - f[j] - g[j];
-            }
-            upk2(mul2(pk2(det[2 * q], det[2 * q + 1]), pk2(lt[2 * q], lt[2 * q + 1])), s[0], s[1]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int k = 2 * q + j;
-                act[k] = (__float_as_int(dett[k]) ^ __float_as_int(s[j] - dett[k])) >= 0;
-                any |= act[k];
-            }
-        }
-        if (!any) {
-            continue;
-        }
-        const float4 u0 = __ldg(up + 0), u1 = __ldg(up + 2), u2 = __ldg(up + 4), u3 = __ldg(up + 6);
-        float px[4], py[4], pz[4], detu[4];
-        any = false;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const f2 ux = q ? pk2(u0.z, u0.w) : pk2(u0.x, u0.y), uy = q ? pk2(u1.z, u1.w) : pk2(u1.x, u1.y);
-            const f2 uz = q ? pk2(u2.z, u2.w) : pk2(u2.x, u2.y), uw = q ? pk2(u3.z, u3.w) : pk2(u3.x, u3.y);
-            const f2 det2 = pk2(det[2 * q], det[2 * q + 1]), dett2 = pk2(dett[2 * q], dett[2 * q + 1]);
-            float a[2], b[2];
-            upk2(mul2(det2, rox), a[0], a[1]);
-            upk2(mul2(dett2, rdx), b[0], b[1]);
-            px[2 * q] = a[0] + b[0];
-            px[2 * q + 1] = a[1] + b[1];
-            upk2(mul2(det2, roy), a[0], a[1]);
-            upk2(mul2(dett2, rdy), b[0], b[1]);
-            py[2 * q] = a[0] + b[0];
-            py[2 * q + 1] = a[1] + b[1];
-            upk2(mul2(det2, roz), a[0], a[1]);
-            upk2(mul2(dett2, rdz), b[0], b[1]);
-            pz[2 * q] = a[0] + b[0];
-            pz[2 * q + 1] = a[1] + b[1];
-            float c[2], d[2];
-            upk2(mul2(pk2(px[2 * q], px[2 * q + 1]), ux), a[0], a[1]);
-            upk2(mul2(pk2(py[2 * q], py[2 * q + 1]), uy), b[0], b[1]);
-            upk2(mul2(pk2(pz[2 * q], pz[2 * q + 1]), uz), c[0], c[1]);
-            upk2(mul2(det2, uw), d[0], d[1]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int k = 2 * q + j;
-                detu[k] = a[j] + b[j] + c[j] + d[j];
-                act[k] = act[k] && ((__float_as_int(detu[k]) ^ __float_as_int(det[k] - detu[k])) >= 0);
-                any |= act[k];
-            }
-        }
-        if (!any) {
-            continue;
-        }
-        const float4 w0 = __ldg(vp + 0), w1 = __ldg(vp + 2), w2 = __ldg(vp + 4), w3 = __ldg(vp + 6);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const f2 vx = q ? pk2(w0.z, w0.w) : pk2(w0.x, w0.y), vy = q ? pk2(w1.z, w1.w) : pk2(w1.x, w1.y);
-            const f2 vz = q ? pk2(w2.z, w2.w) : pk2(w2.x, w2.y), vw = q ? pk2(w3.z, w3.w) : pk2(w3.x, w3.y);
-            float a[2], b[2], c[2], d[2];
-            upk2(mul2(pk2(px[2 * q], px[2 * q + 1]), vx), a[0], a[1]);
-            upk2(mul2(pk2(py[2 * q], py[2 * q + 1]), vy), b[0], b[1]);
-            upk2(mul2(pk2(pz[2 * q], pz[2 * q + 1]), vz), c[0], c[1]);
-            upk2(mul2(pk2(det[2 * q], det[2 * q + 1]), vw), d[0], d[1]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int k = 2 * q + j;
-                const float detv = a[j] + b[j] + c[j] + d[j];
-                if (act[k] && ((__float_as_int(detv) ^ __float_as_int(det[k] - detu[k] - detv)) >= 0)) {
-                    const float rdet = 1.0f / det[k];
-                    const int idx = prim_base + half * 4 + k;
-                    lp[k] = (det[k] < 0.0f) ? idx : (-idx - 1);
-                    lt[k] = dett[k] * rdet;
-                    lu[k] = detu[k] * rdet;
-                    lv[k] = detv * rdet;
-                    any_lane[k] = true;
-                }
-            }
-        }
-    }
-    const float min_t = fminf(lt[0], fminf(lt[1], fminf(lt[2], lt[3])));
-    // the lowest lane holding the minimum wins (explicit select chain: no dynamically indexed local arrays)
-    bool found = false;
-#pragma unroll
-    for (int k = 3; k >= 0; --k) {
-        if (any_lane[k] && lt[k] == min_t) {
-            inter.prim = lp[k];
-            inter.t = lt[k];
-            inter.u = lu[k];
-            inter.v = lv[k];
-            found = true;
-        }
-    }
-    (void)found;
-}
-
 // ---- cooperative leaf test: 4 lanes per (ray, 8-triangle block) ----------------------------------------------------
 // Device triangle copy (k_build_dmtris): block b = 384 bytes, sub-lane k in 0..3 owns bytes [96 k, 96 k + 96) =
 //   {nx nx' ny ny'} {nz nz' nw nw'} {ux ux' uy uy'} {uz uz' uw uw'} {vx vx' vy vy'} {vz vz' vw vw'}
@@ -402,7 +261,9 @@ __global__ void k_build_dmtris(const MTri *__restrict__ src, float4 *__restrict_
 }
 
 // One lane's share of the 8-wide test: triangle k against t_in, then triangle k + 4 against the lane's updated t.
-// Same operations in the same order as intersect_mtri (rt_traverse.cuh); multiplications two triangles per FMUL2,
+// Reference IntersectTri(mtri_accel_t) CoreRef.cpp:54-119, same operations in the same order; multiplications two triangles per FMUL2
+// (the additions stay scalar: ptxas contracts a packed multiply feeding a packed add into FFMA2 even for mul.rn /
+// add.rn.f32x2 and with --fmad=false (CUDA 12.9), which would change the rounding),
 // additions scalar (see the note on FFMA2 contraction above).  Returns whether the lane recorded a hit; t/u/v/prim
 // then hold the lane's final record (lt, lu, lv, lp of the reference).
 RT_DEV bool tri_pair_test(const float4 *__restrict__ q, v3 ro, v3 rd, float t_in, int prim_k, float &t, float &u, float &v,
