@@ -368,9 +368,18 @@ void Renderer::DenoiseImage(const RegionContext &region) {
 }
 // reference internal/RendererCPU.h:790-1007: one pass of the 16-pass UNet filter (rt_unet.cuh)
 void Renderer::DenoiseImage(const int pass, const RegionContext &region) {
-    if (comm_) {
-        log_->Error("Ray(CUDA): the UNet filter is not available on a multi-device renderer yet");
-        return;
+    if (comm_ && pass <= 0) {
+        // the network runs on device 0 (its receptive field spans the whole frame): bring the planes the first pass
+        // reads there over NVLink; the later passes work on device 0's tensors
+        const rc_rect frame{0, 0, w_, h_};
+        for (const int plane : {RC_BUF_FULL, RC_BUF_BASE_COLOR, RC_BUF_DEPTH_NORMALS}) {
+            if (rc_gather_device(comm_, plane, &frame) != 0) {
+                log_->Error("Ray(CUDA): %s", rc_comm_last_error(comm_));
+                return;
+            }
+        }
+        frame_on_dev0_ = true;
+        base_dirty_ = dn_dirty_ = true;
     }
     const rect_t &r = region.rect();
     const rc_rect rr = {r.x, r.y, r.w, r.h};

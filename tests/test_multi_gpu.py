@@ -1,6 +1,6 @@
 """GPU (needs >= 2 devices, skipped otherwise): the frame sharded over several GPUs of one process (rc_comm_* behind
 RendererBase) is the SAME image as one GPU's, bit for bit -- full-frame regions, interleaved sub-regions with their own
-iteration counters, and the NLM denoise that has to see across the band borders."""
+iteration counters, the NLM denoise that has to see across the band borders, and the UNet denoise that runs on device 0 after a peer gather."""
 import numpy as np
 import pytest
 
@@ -20,7 +20,7 @@ def _n_devices():
 @pytest.mark.parametrize("make", [lambda: scenes.cornell_box(96, 70),
                                   lambda: scenes.hall("principled", 160, 90, floor_res=32, n_columns=6, col_seg=10,
                                                       col_rings=6, extra_lights=6)])
-def test_multi_device_frame_equals_single_device_frame(make):
+def test_multi_device_frame_equals_single_device_frame(make, oracle_mod):
     desc = make()
     w, h, spp = desc.width, desc.height, 5
     n = min(_n_devices(), 8)
@@ -54,6 +54,13 @@ def test_multi_device_frame_equals_single_device_frame(make):
     one.denoise((0, 0, w, h), its1[0])
     many.denoise((0, 0, w, h), itsn[0])
     assert many.pixels(host.RAW).tobytes() == one.pixels(host.RAW).tobytes()
+    # UNet denoise: the whole network runs on device 0 after its input planes were gathered there
+    layers = oracle_mod.unet_layers()
+    for r_, it_ in ((one, its1[0]), (many, itsn[0])):
+        r_.set_unet_weights(layers, capi.RC_UNET_FP32)
+        r_.denoise_unet((0, 0, w, h), it_)
+    assert many.pixels(host.RAW).tobytes() == one.pixels(host.RAW).tobytes()
+    assert many.pixels(host.FINAL).tobytes() == one.pixels(host.FINAL).tobytes()
     for x in (s1, sn):
         x.close()
     one.close()
