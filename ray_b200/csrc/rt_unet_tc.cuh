@@ -25,7 +25,8 @@
 // activation ring keeps it resident for the CTA's lifetime.  1080p, all 16 layers: 2.1 ms (first build, one CTA per tile
 // and separate gather passes: 4.7 ms; fp32 path: 31 ms).  Measured and not kept: weights resident with ONE CTA per SM
 // for the 147 KB filter of dec_conv1a (fewer bytes in flight per SM: slower), L2 tensor prefetch one tile ahead (no gain:
-// the loads are bound by L2 -> SMEM throughput, ~11 TB/s, not by DRAM latency).
+// the loads are bound by L2 -> SMEM throughput, ~11 TB/s, not by DRAM latency), 64 / 32-byte swizzled boxes for the thin
+// tensors (correct, not faster).
 #pragma once
 
 #include <cuda.h>
