@@ -24,6 +24,9 @@ import sys
 import threading
 import time
 
+# NCCL writes its banner / debug lines to stdout by default: stdout carries the ONE JSON line of the contract and nothing else
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
