@@ -11,10 +11,17 @@ rays = rays handed to the closest-hit trace (primary + every bounce), from devic
 
 value   : whole-job Mrays/s with the scene resident in HBM, K steps enqueued back to back, timed with CUDA events on the
           launching stream (max over ranks), one framebuffer gather per sample batch inside the timed region when N > 1.
-e2e     : the same metric through the public API one blocking call at a time -- RendererBase::RenderScene with a
-          host->device re-upload of every scene array and a device->host read of the frame (get_raw_pixels_ref) per step.
+e2e     : the same metric through the public API one blocking call at a time -- RendererBase::RenderScene (pass
+          descriptor host->device) and a device->host read of the whole frame into page-locked memory per step (N = 1:
+          the renderer's mirror, as get_raw_pixels_ref; N > 1: every rank copies its strip into ONE shared page-locked
+          host frame over its own PCIe link, then a barrier).  The unchanged scene is not re-uploaded per step (a real
+          caller does not either); one upload + one step is timed separately (scene_upload_plus_one_step_ms).
 N > 1   : weak scaling -- the frame grows to 1920 x (1080 N) and rank r renders rows [1080 r, 1080 (r+1)) of it; no
-          inter-bounce communication, one NCCL gather of the accumulated strips per sample batch.
+          inter-bounce communication; the device-timed arm keeps one NCCL gather of the strips per sample batch, the e2e
+          arm delivers to the host as above.  `strong_scaling`: ONE 1920x1080 frame split over the N ranks.
+configs : at N = 1 the other BASELINE.json configs (#1 Cornell 256^2, #3 hall-principled, #5 instanced 4096^2) are measured
+          in the same run and reported as sub-objects; `cpu_baseline` = the reference's AVX-512 renderer on the host cores
+          this process may really use (affinity and cgroup quota), on a bounded sample of the same workload.
 """
 import argparse
 import json
