@@ -81,8 +81,9 @@ typedef struct rc_scene_view {
     float sky_map_spread_angle; /* must be 0: the procedural sky is out of scope */
     /* Cpu::Scene::GetBounds (ray-sort grid) */
     float bounds_min[3], bounds_max[3];
-    /* textures referenced by materials / triangle lights (NULL / 0 for an untextured scene).  YCoCg-coded textures
-     * (TEX_YCOCG_BIT, only produced with texture compression on) are rejected. */
+    /* textures referenced by materials / triangle lights (NULL / 0 for an untextured scene).  Texels arrive decoded
+     * (BCn through TexStorage::Fetch); YCoCg-coded colour textures (TEX_YCOCG_BIT in the handle, produced when texture
+     * compression is on) are converted on the device after the fetch. */
     const rc_texture *textures;
     uint32_t texture_count;
     /* environment map sampling (environment_t, Core.h:393-410): rotations in radians and the importance-sampling
