@@ -98,6 +98,8 @@ class SharedHostFrame:
             # kill the writers with SIGBUS later, so check the space first and tell every rank when sharing is off
             try:
                 import os
+                if os.environ.get("RAY_B200_NO_SHARED_FRAME"):
+                    raise OSError("disabled by RAY_B200_NO_SHARED_FRAME")
                 st = os.statvfs("/dev/shm")
                 if st.f_bavail * st.f_frsize < self.nbytes + (64 << 20):
                     raise OSError("/dev/shm has %d MB free, the frame needs %d MB" % (st.f_bavail * st.f_frsize >> 20, self.nbytes >> 20))

@@ -90,6 +90,40 @@ def test_shared_host_frame_world2_gloo(tmp_path, h):
     assert np.array_equal(frame, want.astype(np.float32))
 
 
+def _private_worker(rank, world, port, w, h, out_dir):
+    import torch.distributed as tdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["RAY_B200_NO_SHARED_FRAME"] = "1"
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    frame = rdist.SharedHostFrame(w, h, pin=False)
+    assert frame.shared is False and frame.array.shape == (h, w, 4)
+    x, y, ww, hh = rdist.strip_rect(rank, world, w, h)
+    frame.rows(y, hh)[...] = float(rank + 1)
+    tdist.barrier()
+    # private frames: the other rank's strip was NOT written here
+    other = rdist.strip_rect(1 - rank, world, w, h)
+    assert float(np.abs(frame.rows(other[1], other[3])).max()) == 0.0
+    np.save(os.path.join(out_dir, f"private{rank}.npy"), np.array(frame.array))
+    frame.close()
+    tdist.destroy_process_group()
+
+
+def test_shared_host_frame_falls_back_to_private_strips(tmp_path):
+    """No room in /dev/shm (forced here): every rank keeps a private frame and delivers its own strip; nobody hangs."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    w, h, world = 7, 10, 2
+    mp.spawn(_private_worker, args=(world, port, w, h, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        a = np.load(tmp_path / f"private{rank}.npy")
+        x, y, ww, hh = rdist.strip_rect(rank, world, w, h)
+        assert (a[y:y + hh] == float(rank + 1)).all()
+
+
 def test_comm_bands_partition_any_rect():
     """rc_comm_strip (pure arithmetic of the C-ABI): bands of the frame tile it exactly; heights differ by <= 1 row."""
     import ctypes as C
